@@ -1,0 +1,104 @@
+// bellman_b200 internal: context, device memory cache, error plumbing.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/bellman_b200.h"
+#include "curve.cuh"
+
+namespace bb {
+
+void set_error(const char* fmt, ...);
+
+#define BB_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            bb::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return BB_ERR_CUDA;                                                               \
+        }                                                                                     \
+    } while (0)
+
+#define BB_TRY(call)                       \
+    do {                                   \
+        int s__ = (call);                  \
+        if (s__ != BB_OK) return s__;      \
+    } while (0)
+
+struct NttTables;
+
+}  // namespace bb
+
+// Context = one device.  Device allocations are cached by size so that the steady state of a
+// prover issues no cudaMalloc/cudaFree (both synchronise the device).
+struct bb_ctx {
+    int device = 0;
+    int num_sms = 0;
+    std::mutex mu;
+    std::multimap<size_t, void*> free_blocks;
+    std::map<void*, size_t> live_blocks;
+    std::vector<cudaStream_t> streams;       // round-robin pool for async jobs
+    size_t next_stream = 0;
+    cudaStream_t main_stream = nullptr;
+    std::atomic<uint64_t> launches{0};
+    long opt_msm_window_bits = 0;
+    long opt_ntt_tile_log = 11;
+    long opt_ntt_col_bits = 3;
+    std::map<uint32_t, bb::NttTables*> ntt_tables;   // by log_n
+
+    int alloc(size_t bytes, void** out);
+    void release(void* p);
+    cudaStream_t pick_stream();
+    void count_launch(uint64_t k = 1) { launches.fetch_add(k, std::memory_order_relaxed); }
+};
+
+struct bb_bases {
+    bb_ctx* ctx;
+    int group;
+    void* d_points;          // Affine<Fp> or Affine<Fp2>
+    size_t n;                // points held here
+    size_t global_offset;    // first global index held
+    size_t global_len;       // length of the whole (unsharded) vector
+};
+
+namespace bb {
+
+// RAII device buffer from the context cache
+struct DevBuf {
+    bb_ctx* ctx = nullptr;
+    void* p = nullptr;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { reset(); }
+    int alloc(bb_ctx* c, size_t bytes) { reset(); ctx = c; return c->alloc(bytes ? bytes : 16, &p); }
+    void reset() { if (p && ctx) ctx->release(p); p = nullptr; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// ---- ntt.cu ----
+int ntt_run_device(bb_ctx* ctx, cudaStream_t st, Fr* d_data, Fr* d_tmp, uint32_t log_n, int mode);
+int h_poly_device(bb_ctx* ctx, cudaStream_t st, Fr* d_a, Fr* d_b, Fr* d_c, Fr* d_tmp, uint32_t log_m);
+int fr_convert_device(bb_ctx* ctx, cudaStream_t st, Fr* d_data, size_t n, bool to_montgomery);
+
+// ---- msm.cu ----
+struct MsmResult {
+    int status = BB_OK;
+    bool g2 = false;
+    G1X g1;
+    G2X x2;
+};
+int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint64_t* density_bits, size_t density_len,
+              const void* scalars, bool scalars_on_device, size_t n, int form, cudaEvent_t wait_for, bb_msm_job** out);
+int msm_wait_result(bb_msm_job* job, MsmResult* res);
+
+}  // namespace bb

@@ -1,0 +1,404 @@
+// bellman_b200: C-ABI entry points that are not MSM / prover specific (include/bellman_b200.h).
+#include "bb_internal.cuh"
+
+using namespace bb;
+
+namespace bb {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+void g1_compress(const G1Affine& p, uint8_t* out);
+void g2_compress(const G2Affine& p, uint8_t* out);
+G1X g1_host_mul(const G1X& p, const uint32_t* k);
+G2X g2_host_mul(const G2X& p, const uint32_t* k);
+}  // namespace bb
+
+int bb_ctx::alloc(size_t bytes, void** out) {
+    // round up so that slightly different sizes share cached blocks
+    size_t want = (bytes + 255) & ~(size_t)255;
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = free_blocks.lower_bound(want);
+        if (it != free_blocks.end() && it->first <= want + want / 4 + 4096) {
+            *out = it->second;
+            live_blocks[it->second] = it->first;
+            free_blocks.erase(it);
+            return BB_OK;
+        }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        // drop the cache and retry once
+        {
+            std::lock_guard<std::mutex> g(mu);
+            for (auto& kv : free_blocks) cudaFree(kv.second);
+            free_blocks.clear();
+        }
+        cudaGetLastError();
+        e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { set_error("cudaMalloc(%zu): %s", want, cudaGetErrorString(e)); cudaGetLastError(); return BB_ERR_OOM; }
+    }
+    std::lock_guard<std::mutex> g(mu);
+    live_blocks[p] = want;
+    *out = p;
+    return BB_OK;
+}
+void bb_ctx::release(void* p) {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = live_blocks.find(p);
+    if (it == live_blocks.end()) return;
+    free_blocks.emplace(it->second, p);
+    live_blocks.erase(it);
+}
+cudaStream_t bb_ctx::pick_stream() {
+    std::lock_guard<std::mutex> g(mu);
+    cudaStream_t s = streams[next_stream % streams.size()];
+    next_stream++;
+    return s;
+}
+
+namespace {
+
+// fixed-base tables for bb_fixed_base_mul: table[w*255 + d-1] = d * 2^(8w) * G, affine
+template <class F>
+struct FixedTable {
+    Affine<F>* d_table = nullptr;
+};
+FixedTable<Fp> g_tab1;
+FixedTable<Fp2> g_tab2;
+std::mutex g_tab_mu;
+
+template <class F>
+void batch_to_affine_host(const std::vector<XYZZ<F>>& in, std::vector<Affine<F>>& out) {
+    size_t n = in.size();
+    out.resize(n);
+    std::vector<F> pre(n);
+    F acc = FieldOps<F>::one();
+    for (size_t i = 0; i < n; i++) { pre[i] = acc; acc = acc * in[i].ZZZ; }       // no identities in the table
+    F inv = FieldOps<F>::inv(acc);
+    for (size_t i = n; i-- > 0;) {
+        F zi3 = inv * pre[i];
+        inv = inv * in[i].ZZZ;
+        F zi2 = (zi3 * in[i].ZZ).sqr();
+        out[i] = {in[i].X * zi2, in[i].Y * zi3};
+    }
+}
+
+template <class F>
+int build_fixed_table(FixedTable<F>& t, const Affine<F>& gen) {
+    if (t.d_table) return BB_OK;
+    std::vector<XYZZ<F>> pts(32 * 255);
+    XYZZ<F> base = XYZZ<F>::from_affine(gen);
+    for (int w = 0; w < 32; w++) {
+        XYZZ<F> cur = base;
+        for (int d = 1; d <= 255; d++) { pts[w * 255 + d - 1] = cur; cur.add(base); }
+        base = cur;
+    }
+    std::vector<Affine<F>> aff;
+    batch_to_affine_host(pts, aff);
+    BB_CUDA(cudaMalloc(&t.d_table, aff.size() * sizeof(Affine<F>)));
+    BB_CUDA(cudaMemcpy(t.d_table, aff.data(), aff.size() * sizeof(Affine<F>), cudaMemcpyHostToDevice));
+    return BB_OK;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_fixed_base_mul(const Affine<F>* __restrict__ table, const Fr* scalars, size_t n, int montgomery,
+                                                        Affine<F>* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr s = scalars[i];
+    if (montgomery) s = fr_to_canonical(s);
+    XYZZ<F> acc = XYZZ<F>::identity();
+    for (int w = 0; w < 32; w++) {
+        uint32_t d = (s.l[w >> 2] >> (8 * (w & 3))) & 0xffu;
+        if (d) acc.add_mixed(table[w * 255 + d - 1]);
+    }
+    out[i] = acc.to_affine();
+}
+
+template <class F>
+int fixed_base_mul(bb_ctx* ctx, FixedTable<F>& tab, const Affine<F>& gen, const void* scalars, size_t n, int form, void* out) {
+    {
+        std::lock_guard<std::mutex> g(g_tab_mu);
+        BB_TRY(build_fixed_table(tab, gen));
+    }
+    DevBuf d_s, d_o;
+    BB_TRY(d_s.alloc(ctx, n * 32));
+    BB_TRY(d_o.alloc(ctx, n * sizeof(Affine<F>)));
+    cudaStream_t st = ctx->main_stream;
+    BB_CUDA(cudaMemcpyAsync(d_s.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
+    if (n) {
+        k_fixed_base_mul<F><<<cdiv(n, 128), 128, 0, st>>>(tab.d_table, d_s.as<Fr>(), n, form == BB_FORM_MONTGOMERY, d_o.as<Affine<F>>());
+        ctx->count_launch();
+    }
+    BB_CUDA(cudaGetLastError());
+    BB_CUDA(cudaMemcpyAsync(out, d_o.p, n * sizeof(Affine<F>), cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    return BB_OK;
+}
+
+
+// ---- diagnostics: element-wise field / point operations on the device ------------------------
+template <class FE>
+__global__ void k_selftest_field(const FE* a, const FE* b, FE* o, size_t n, int op) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    FE x = a[i], y = b[i];
+    o[i] = op == 0 ? x * y : op == 1 ? x + y : op == 2 ? x - y : x.sqr();
+}
+template <class F>
+__global__ void k_selftest_point(const Affine<F>* a, const Affine<F>* b, Affine<F>* o, size_t n, int op) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    XYZZ<F> x = XYZZ<F>::from_affine(a[i]);
+    if (op == 0) x.add_mixed(b[i]);
+    else if (op == 1) { x = x.dbl(); x.add(XYZZ<F>::from_affine(b[i])); }   // 2a + b through the projective paths
+    else if (op == 2) { XYZZ<F> y = XYZZ<F>::from_affine(b[i]); y = y.dbl(); y.add_mixed(b[i].neg()); x.add(y); }  // a + (2b - b)
+    o[i] = x.to_affine();
+}
+template <class T, class K>
+int selftest_run(bb_ctx* ctx, K kernel, const void* a, const void* b, void* o, size_t n, int op) {
+    DevBuf da, db, d_o2;
+    BB_TRY(da.alloc(ctx, n * sizeof(T))); BB_TRY(db.alloc(ctx, n * sizeof(T))); BB_TRY(d_o2.alloc(ctx, n * sizeof(T)));
+    cudaStream_t st = ctx->main_stream;
+    BB_CUDA(cudaMemcpyAsync(da.p, a, n * sizeof(T), cudaMemcpyHostToDevice, st));
+    BB_CUDA(cudaMemcpyAsync(db.p, b, n * sizeof(T), cudaMemcpyHostToDevice, st));
+    if (n) { kernel<<<cdiv(n, 64), 64, 0, st>>>(da.as<T>(), db.as<T>(), d_o2.as<T>(), n, op); ctx->count_launch(); }
+    BB_CUDA(cudaGetLastError());
+    BB_CUDA(cudaMemcpyAsync(o, d_o2.p, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    return BB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bb_last_error(void) { return g_err; }
+int bb_version(void) { return 100; }
+
+int bb_ctx_create(int device, bb_ctx** out) {
+    if (!out) { set_error("bb_ctx_create: null out"); return BB_ERR_ARG; }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error("no usable CUDA device (%s); bellman_b200 has no CPU fallback", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return BB_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) { set_error("device %d out of range (%d devices)", device, count); return BB_ERR_ARG; }
+    BB_CUDA(cudaSetDevice(device));
+    bb_ctx* ctx = new bb_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    BB_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->num_sms = prop.multiProcessorCount;
+    BB_CUDA(cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++) {
+        cudaStream_t s;
+        BB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        ctx->streams.push_back(s);
+    }
+    *out = ctx;
+    return BB_OK;
+}
+
+void bb_ctx_destroy(bb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
+    for (auto& kv : ctx->live_blocks) cudaFree(kv.first);
+    for (auto s : ctx->streams) cudaStreamDestroy(s);
+    if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
+    // NTT tables are freed with the process; they are keyed by size and shared
+    delete ctx;
+}
+
+int bb_ctx_set_option(bb_ctx* ctx, const char* key, long value) {
+    if (!ctx || !key) { set_error("bb_ctx_set_option: null argument"); return BB_ERR_ARG; }
+    std::string k(key);
+    if (k == "msm_window_bits") ctx->opt_msm_window_bits = value;
+    else if (k == "ntt_tile_log") ctx->opt_ntt_tile_log = value;
+    else if (k == "ntt_col_bits") ctx->opt_ntt_col_bits = value;
+    else { set_error("unknown option %s", key); return BB_ERR_ARG; }
+    return BB_OK;
+}
+
+int bb_ctx_synchronize(bb_ctx* ctx) {
+    if (!ctx) return BB_ERR_ARG;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    BB_CUDA(cudaDeviceSynchronize());
+    return BB_OK;
+}
+
+uint64_t bb_ctx_kernel_launches(const bb_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+int bb_device_alloc(bb_ctx* ctx, size_t bytes, void** d_out) {
+    if (!ctx || !d_out) return BB_ERR_ARG;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    return ctx->alloc(bytes, d_out);
+}
+int bb_device_free(bb_ctx* ctx, void* d_ptr) {
+    if (!ctx) return BB_ERR_ARG;
+    if (d_ptr) ctx->release(d_ptr);
+    return BB_OK;
+}
+int bb_device_upload(bb_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+    if (!ctx) return BB_ERR_ARG;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    BB_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->main_stream));
+    BB_CUDA(cudaStreamSynchronize(ctx->main_stream));
+    return BB_OK;
+}
+int bb_device_download(bb_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+    if (!ctx) return BB_ERR_ARG;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    BB_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->main_stream));
+    BB_CUDA(cudaStreamSynchronize(ctx->main_stream));
+    return BB_OK;
+}
+
+int bb_ntt_device(bb_ctx* ctx, void* d_fr_inout, uint32_t log_n, int mode) {
+    if (!ctx || !d_fr_inout) { set_error("bb_ntt_device: null argument"); return BB_ERR_ARG; }
+    if (log_n >= (uint32_t)bbc::FR_S) { set_error("PolynomialDegreeTooLarge"); return BB_ERR_POLYNOMIAL_DEGREE_TOO_LARGE; }
+    BB_CUDA(cudaSetDevice(ctx->device));
+    DevBuf tmp;
+    BB_TRY(tmp.alloc(ctx, (size_t)32 << log_n));
+    BB_TRY(ntt_run_device(ctx, ctx->main_stream, (Fr*)d_fr_inout, tmp.as<Fr>(), log_n, mode));
+    BB_CUDA(cudaStreamSynchronize(ctx->main_stream));
+    return BB_OK;
+}
+
+int bb_ntt(bb_ctx* ctx, void* fr_inout, uint32_t log_n, int mode, int form) {
+    if (!ctx || !fr_inout) { set_error("bb_ntt: null argument"); return BB_ERR_ARG; }
+    if (log_n >= (uint32_t)bbc::FR_S) { set_error("PolynomialDegreeTooLarge"); return BB_ERR_POLYNOMIAL_DEGREE_TOO_LARGE; }
+    BB_CUDA(cudaSetDevice(ctx->device));
+    size_t n = (size_t)1 << log_n;
+    DevBuf d, tmp;
+    BB_TRY(d.alloc(ctx, n * 32));
+    BB_TRY(tmp.alloc(ctx, n * 32));
+    cudaStream_t st = ctx->main_stream;
+    BB_CUDA(cudaMemcpyAsync(d.p, fr_inout, n * 32, cudaMemcpyHostToDevice, st));
+    // the transform is linear, so canonical inputs can be transformed as they are (the
+    // twiddles carry the Montgomery factor); only the fused multiplications by table entries
+    // are Montgomery products, which is exactly what keeps a canonical vector canonical.
+    (void)form;
+    BB_TRY(ntt_run_device(ctx, st, d.as<Fr>(), tmp.as<Fr>(), log_n, mode));
+    BB_CUDA(cudaMemcpyAsync(fr_inout, d.p, n * 32, cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    return BB_OK;
+}
+
+int bb_h_poly(bb_ctx* ctx, const void* a, const void* b, const void* c, size_t n, void* h_out, size_t* m_out) {
+    if (!ctx || !h_out || (n && (!a || !b || !c))) { set_error("bb_h_poly: null argument"); return BB_ERR_ARG; }
+    BB_CUDA(cudaSetDevice(ctx->device));
+    size_t m = 1;
+    uint32_t log_m = 0;
+    while (m < n) {
+        m *= 2;
+        log_m++;
+        if (log_m >= (uint32_t)bbc::FR_S) { set_error("PolynomialDegreeTooLarge"); return BB_ERR_POLYNOMIAL_DEGREE_TOO_LARGE; }
+    }
+    DevBuf d_a, d_b, d_c, d_t;
+    BB_TRY(d_a.alloc(ctx, m * 32)); BB_TRY(d_b.alloc(ctx, m * 32)); BB_TRY(d_c.alloc(ctx, m * 32)); BB_TRY(d_t.alloc(ctx, m * 32));
+    cudaStream_t st = ctx->main_stream;
+    const void* srcs[3] = {a, b, c};
+    DevBuf* dst[3] = {&d_a, &d_b, &d_c};
+    for (int k = 0; k < 3; k++) {
+        if (m > n) BB_CUDA(cudaMemsetAsync((char*)dst[k]->p + n * 32, 0, (m - n) * 32, st));
+        if (n) BB_CUDA(cudaMemcpyAsync(dst[k]->p, srcs[k], n * 32, cudaMemcpyHostToDevice, st));
+    }
+    BB_TRY(h_poly_device(ctx, st, d_a.as<Fr>(), d_b.as<Fr>(), d_c.as<Fr>(), d_t.as<Fr>(), log_m));
+    BB_TRY(fr_convert_device(ctx, st, d_a.as<Fr>(), m - 1, false));
+    if (m > 1) BB_CUDA(cudaMemcpyAsync(h_out, d_a.p, (m - 1) * 32, cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    if (m_out) *m_out = m;
+    return BB_OK;
+}
+
+int bb_bases_upload(bb_ctx* ctx, int group, const void* affine, size_t n, size_t global_offset, size_t global_len, bb_bases** out) {
+    if (!ctx || !out || (n && !affine) || (group != BB_G1 && group != BB_G2)) { set_error("bb_bases_upload: bad argument"); return BB_ERR_ARG; }
+    if (global_offset + n > global_len) { set_error("bb_bases_upload: shard [%zu,%zu) exceeds %zu", global_offset, global_offset + n, global_len); return BB_ERR_ARG; }
+    BB_CUDA(cudaSetDevice(ctx->device));
+    size_t stride = group == BB_G1 ? sizeof(G1Affine) : sizeof(G2Affine);
+    void* d = nullptr;
+    BB_TRY(ctx->alloc((n ? n : 1) * stride, &d));
+    if (n) {
+        BB_CUDA(cudaMemcpyAsync(d, affine, n * stride, cudaMemcpyHostToDevice, ctx->main_stream));
+        BB_CUDA(cudaStreamSynchronize(ctx->main_stream));
+    }
+    bb_bases* b = new bb_bases();
+    b->ctx = ctx; b->group = group; b->d_points = d; b->n = n; b->global_offset = global_offset; b->global_len = global_len;
+    *out = b;
+    return BB_OK;
+}
+void bb_bases_free(bb_bases* b) {
+    if (!b) return;
+    if (b->d_points) b->ctx->release(b->d_points);
+    delete b;
+}
+
+int bb_point_add(int group, const void* a, const void* b, void* out) {
+    if (!a || !b || !out) return BB_ERR_ARG;
+    if (group == BB_G1) {
+        G1Affine pa, pb; std::memcpy(&pa, a, 96); std::memcpy(&pb, b, 96);
+        G1X x = G1X::from_affine(pa); x.add_mixed(pb);
+        G1Affine r = x.to_affine(); std::memcpy(out, &r, 96);
+    } else if (group == BB_G2) {
+        G2Affine pa, pb; std::memcpy(&pa, a, 192); std::memcpy(&pb, b, 192);
+        G2X x = G2X::from_affine(pa); x.add_mixed(pb);
+        G2Affine r = x.to_affine(); std::memcpy(out, &r, 192);
+    } else return BB_ERR_ARG;
+    return BB_OK;
+}
+int bb_point_mul(int group, const void* a, const void* k, int form, void* out) {
+    if (!a || !k || !out) return BB_ERR_ARG;
+    Fr s; std::memcpy(s.l, k, 32);
+    if (form == BB_FORM_MONTGOMERY) s = fr_to_canonical(s);
+    if (group == BB_G1) {
+        G1Affine pa; std::memcpy(&pa, a, 96);
+        G1Affine r = g1_host_mul(G1X::from_affine(pa), s.l).to_affine(); std::memcpy(out, &r, 96);
+    } else if (group == BB_G2) {
+        G2Affine pa; std::memcpy(&pa, a, 192);
+        G2Affine r = g2_host_mul(G2X::from_affine(pa), s.l).to_affine(); std::memcpy(out, &r, 192);
+    } else return BB_ERR_ARG;
+    return BB_OK;
+}
+int bb_point_compress(int group, const void* a, uint8_t* out) {
+    if (!a || !out) return BB_ERR_ARG;
+    if (group == BB_G1) { G1Affine p; std::memcpy(&p, a, 96); g1_compress(p, out); }
+    else if (group == BB_G2) { G2Affine p; std::memcpy(&p, a, 192); g2_compress(p, out); }
+    else return BB_ERR_ARG;
+    return BB_OK;
+}
+int bb_fixed_base_mul(bb_ctx* ctx, int group, const void* scalars, size_t n, int form, void* out) {
+    if (!ctx || (n && (!scalars || !out))) { set_error("bb_fixed_base_mul: null argument"); return BB_ERR_ARG; }
+    BB_CUDA(cudaSetDevice(ctx->device));
+    if (group == BB_G1) return fixed_base_mul<Fp>(ctx, g_tab1, g1_generator(), scalars, n, form, out);
+    if (group == BB_G2) return fixed_base_mul<Fp2>(ctx, g_tab2, g2_generator(), scalars, n, form, out);
+    set_error("bad group");
+    return BB_ERR_ARG;
+}
+
+int bb_selftest_field(bb_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n) {
+    if (!ctx) return BB_ERR_ARG;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    if (field == 0) return selftest_run<Fr>(ctx, k_selftest_field<Fr>, a, b, out, n, op);
+    if (field == 1) return selftest_run<Fp>(ctx, k_selftest_field<Fp>, a, b, out, n, op);
+    return BB_ERR_ARG;
+}
+int bb_selftest_point(bb_ctx* ctx, int group, int op, const void* a, const void* b, void* out, size_t n) {
+    if (!ctx) return BB_ERR_ARG;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    if (group == BB_G1) return selftest_run<G1Affine>(ctx, k_selftest_point<Fp>, a, b, out, n, op);
+    if (group == BB_G2) return selftest_run<G2Affine>(ctx, k_selftest_point<Fp2>, a, b, out, n, op);
+    return BB_ERR_ARG;
+}
+
+}  // extern "C"

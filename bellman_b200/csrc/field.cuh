@@ -1,0 +1,115 @@
+// bellman_b200: BLS12-381 Fr / Fp / Fp2 on top of mp.cuh.
+// Fr is the field EvaluationDomain works over (/root/reference/src/domain.rs:21-28)
+// and the scalar field of multiexp (src/multiexp.rs:305-316); Fp / Fp2 are the
+// coordinate fields of G1 / G2.
+#pragma once
+#include "bls_constants.cuh"
+#include "mp.cuh"
+
+namespace bb {
+
+// per-translation-unit copies of the moduli in constant memory: operands of the
+// reduction rows come straight from the constant bank, no registers.
+static __device__ __constant__ uint32_t kFrMod[8] = {BBC_FR_MOD_LIST};
+static __device__ __constant__ uint32_t kFpMod[12] = {BBC_FP_MOD_LIST};
+
+struct FrCfg {
+    static constexpr int N = 8;
+    static constexpr uint32_t INV = bbc::FR_INV;
+    static constexpr uint64_t INV64 = 0xfffffffeffffffffull;
+#if defined(__CUDACC__)
+    static __device__ __forceinline__ uint32_t dmod(int k) { return kFrMod[k]; }
+#endif
+    static const uint32_t* hmod() { return bbc::FR_MOD; }
+};
+struct FpCfg {
+    static constexpr int N = 12;
+    static constexpr uint32_t INV = bbc::FP_INV;
+    static constexpr uint64_t INV64 = 0x89f3fffcfffcfffdull;
+#if defined(__CUDACC__)
+    static __device__ __forceinline__ uint32_t dmod(int k) { return kFpMod[k]; }
+#endif
+    static const uint32_t* hmod() { return bbc::FP_MOD; }
+};
+static_assert((uint32_t)FrCfg::INV64 == FrCfg::INV && (uint32_t)FpCfg::INV64 == FpCfg::INV, "inv");
+
+typedef Fe<FrCfg> Fr;
+typedef Fe<FpCfg> Fp;
+
+BB_HD Fr fr_from_limbs(const uint32_t* p) { Fr r; for (int i = 0; i < 8; i++) r.l[i] = p[i]; return r; }
+BB_HD Fp fp_from_limbs(const uint32_t* p) { Fp r; for (int i = 0; i < 12; i++) r.l[i] = p[i]; return r; }
+
+// constants as immediates (constexpr arrays are not addressable from device code)
+BB_HD Fr fr_one() { return Fr{{BBC_FR_R_LIST}}; }
+BB_HD Fr fr_r2() { return Fr{{BBC_FR_R2_LIST}}; }
+BB_HD Fr fr_generator() { return Fr{{BBC_FR_GENERATOR_M_LIST}}; }
+BB_HD Fr fr_root_of_unity() { return Fr{{BBC_FR_ROOT_OF_UNITY_M_LIST}}; }
+BB_HD Fp fp_one() { return Fp{{BBC_FP_R_LIST}}; }
+BB_HD Fp fp_r2() { return Fp{{BBC_FP_R2_LIST}}; }
+
+BB_HD Fr fr_raw_one() { Fr r = Fr::zero(); r.l[0] = 1; return r; }
+BB_HD Fp fp_raw_one() { Fp r = Fp::zero(); r.l[0] = 1; return r; }
+BB_HD Fr fr_to_canonical(const Fr& a) { return a * fr_raw_one(); }
+BB_HD Fr fr_from_canonical(const Fr& a) { return a * fr_r2(); }
+BB_HD Fp fp_to_canonical(const Fp& a) { return a * fp_raw_one(); }
+BB_HD Fp fp_from_canonical(const Fp& a) { return a * fp_r2(); }
+BB_HD Fr fr_from_u64(uint64_t v) { Fr r = Fr::zero(); r.l[0] = (uint32_t)v; r.l[1] = (uint32_t)(v >> 32); return fr_from_canonical(r); }
+
+// a^(q-2)
+BB_HD Fr fr_inv(const Fr& a) {
+    uint32_t e[8];
+    for (int i = 0; i < 8; i++) e[i] = Fr::modl(i);
+    e[0] -= 2;
+    return a.pow(e, 8, fr_one());
+}
+BB_HD Fp fp_inv(const Fp& a) {
+    uint32_t e[12];
+    for (int i = 0; i < 12; i++) e[i] = Fp::modl(i);
+    e[0] -= 2;
+    return a.pow(e, 12, fp_one());
+}
+
+// Fp2 = Fp[u]/(u^2+1)
+struct Fp2 {
+    Fp c0, c1;
+    BB_HD static Fp2 zero() { return {Fp::zero(), Fp::zero()}; }
+    BB_HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    BB_HD bool operator==(const Fp2& o) const { return c0 == o.c0 && c1 == o.c1; }
+    BB_HD bool operator!=(const Fp2& o) const { return !(*this == o); }
+    BB_HD Fp2 operator+(const Fp2& o) const { return {c0 + o.c0, c1 + o.c1}; }
+    BB_HD Fp2 operator-(const Fp2& o) const { return {c0 - o.c0, c1 - o.c1}; }
+    BB_HD_NOINLINE Fp2 operator*(const Fp2& o) const { // Karatsuba: 3 Fp products
+        Fp aa = c0 * o.c0, bb_ = c1 * o.c1;
+        Fp t = (c0 + c1) * (o.c0 + o.c1);
+        return {aa - bb_, t - aa - bb_};
+    }
+    BB_HD_NOINLINE Fp2 sqr() const {                   // (c0+c1)(c0-c1), 2 c0 c1
+        Fp s = c0 + c1, d = c0 - c1, m = c0 * c1;
+        return {s * d, m + m};
+    }
+    BB_HD Fp2 dbl() const { return {c0.dbl(), c1.dbl()}; }
+    BB_HD Fp2 neg() const { return {c0.neg(), c1.neg()}; }
+    BB_HD Fp2& operator+=(const Fp2& o) { *this = *this + o; return *this; }
+    BB_HD Fp2& operator-=(const Fp2& o) { *this = *this - o; return *this; }
+    BB_HD Fp2& operator*=(const Fp2& o) { *this = *this * o; return *this; }
+};
+BB_HD Fp2 fp2_one() { return {fp_one(), Fp::zero()}; }
+BB_HD Fp2 fp2_inv(const Fp2& a) {
+    Fp n = fp_inv(a.c0.sqr() + a.c1.sqr());
+    return {a.c0 * n, (a.c1 * n).neg()};
+}
+
+// uniform field-trait view used by the curve templates
+template <class F> struct FieldOps;
+template <> struct FieldOps<Fp> {
+    BB_HD static Fp one() { return fp_one(); }
+    BB_HD static Fp inv(const Fp& a) { return fp_inv(a); }
+    static constexpr int WORDS = 12;
+};
+template <> struct FieldOps<Fp2> {
+    BB_HD static Fp2 one() { return fp2_one(); }
+    BB_HD static Fp2 inv(const Fp2& a) { return fp2_inv(a); }
+    static constexpr int WORDS = 24;
+};
+
+}  // namespace bb

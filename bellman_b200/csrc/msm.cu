@@ -1,0 +1,591 @@
+// bellman_b200: Pippenger multi-scalar multiplication over BLS12-381 G1/G2 for sm_100a.
+//
+// Replaces multiexp() / multiexp_inner() (/root/reference/src/multiexp.rs:210-332).  The
+// reference runs one CPU task per c-bit window, each scanning all n scalars and doing a
+// projective += affine per non-zero digit (:242-265), then a serial summation by parts
+// (:271-275) and a serial Horner fold (:295-300).  Here:
+//   1. k_msm_digits   one thread per scalar: canonicalise (Exponent::from, :172-182),
+//                     resolve the base index through the density map (:242-243, bases are
+//                     compacted to set bits), signed-digit recode into W windows (halves the
+//                     bucket count) and histogram the (window, |digit|) keys;
+//   2. scan           exclusive prefix sum of the histogram -> bucket segments;
+//   3. k_msm_digits   again in scatter mode: counting sort of base indices by bucket;
+//   4. k_msm_accumulate  one thread per bucket: gather its affine bases from HBM (32 B
+//                     sector aligned, each read once per window) and sum them with XYZZ
+//                     mixed additions;
+//   5. k_msm_reduce   summation by parts per window, in parallel: every thread owns K
+//                     adjacent buckets (running-sum trick), lifts its partial by its bucket
+//                     offset with a short double-and-add, and the CTA tree-reduces;
+//   6. host           Horner fold of the W window sums (255 doublings), to_affine.
+// Scalars equal to one (Exponent::One, :246-252) bypass the buckets through a list that is
+// summed by a tree, zero scalars (Exponent::Zero, :245) are dropped -- exactly the
+// reference's fast paths, kept because real witnesses are dominated by 0/1.
+// Error semantics (Source::next / skip, :53-86) are reproduced, see bb_msm_wait.
+#include <cmath>
+
+#include "bb_internal.cuh"
+
+namespace bb {
+
+template <class F> struct PointIO;
+template <> struct PointIO<Fp> { static constexpr int VEC = 6; };     // uint4 loads per affine point
+template <> struct PointIO<Fp2> { static constexpr int VEC = 12; };
+
+template <class F>
+__device__ __forceinline__ Affine<F> ld_affine(const Affine<F>* p) {
+    constexpr int V = PointIO<F>::VEC;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    Affine<F> r;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < V; i++) {
+        uint4 v = __ldg(q + i);
+        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+    }
+    return r;
+}
+template <class T>
+__device__ __forceinline__ void st_words(T* dst, const T& v) {
+    constexpr int V = sizeof(T) / 16;
+    uint4* q = reinterpret_cast<uint4*>(dst);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+    for (int i = 0; i < V; i++) q[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+}
+template <class T>
+__device__ __forceinline__ T ld_words(const T* src) {
+    constexpr int V = sizeof(T) / 16;
+    const uint4* q = reinterpret_cast<const uint4*>(src);
+    T r;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < V; i++) {
+        uint4 v = q[i];
+        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+    }
+    return r;
+}
+
+struct DigitArgs {
+    const Fr* scalars;
+    size_t n;
+    int montgomery;
+    const uint64_t* density;        // NULL = FullDensity
+    const uint32_t* density_rank;   // set bits before word j
+    uint64_t base_offset;           // Source start position (global)
+    uint64_t shard_lo, shard_n;     // this device holds global base indices [shard_lo, shard_lo+shard_n)
+    uint64_t global_len;
+    uint32_t c, W;
+    uint32_t* counts;               // mode 0: histogram; mode 1: cursors
+    uint32_t* sorted;               // mode 1
+    uint32_t* ones_list;            // base indices with scalar == 1
+    uint32_t* ones_count;
+    uint32_t* err;                  // [0] = min scalar index hitting EOF (0xffffffff none)
+    int mode;
+};
+
+__device__ __forceinline__ uint32_t extract_bits(const uint32_t* l, uint32_t pos, uint32_t c) {
+    uint32_t word = pos >> 5, off = pos & 31;
+    if (word >= 8) return 0;
+    uint64_t v = l[word];
+    if (word + 1 < 8) v |= (uint64_t)l[word + 1] << 32;
+    return (uint32_t)(v >> off) & ((1u << c) - 1u);
+}
+
+__global__ void __launch_bounds__(256) k_msm_digits(DigitArgs A) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    uint64_t rank = i;
+    if (A.density) {
+        uint64_t word = A.density[i >> 6];
+        if (!((word >> (i & 63)) & 1)) return;                       // multiexp.rs:243
+        rank = (uint64_t)A.density_rank[i >> 6] + __popcll(word & ((1ull << (i & 63)) - 1ull));
+    }
+    uint64_t gi = A.base_offset + rank;
+    if (gi >= A.global_len) {                                        // Source::next/skip EOF, :55-61,74-80
+        atomicMin(&A.err[0], (uint32_t)i);
+        return;
+    }
+    const uint4* q = reinterpret_cast<const uint4*>(A.scalars + i);
+    uint4 lo = q[0], hi = q[1];
+    Fr s;
+    s.l[0] = lo.x; s.l[1] = lo.y; s.l[2] = lo.z; s.l[3] = lo.w;
+    s.l[4] = hi.x; s.l[5] = hi.y; s.l[6] = hi.z; s.l[7] = hi.w;
+    if (A.montgomery) s = fr_to_canonical(s);                        // to_le_bits, :179
+    if (s.is_zero()) return;                                         // Exponent::Zero, :245
+    if (gi < A.shard_lo || gi >= A.shard_lo + A.shard_n) return;     // another device's shard
+    uint32_t local = (uint32_t)(gi - A.shard_lo);
+    uint32_t rest = s.l[1] | s.l[2] | s.l[3] | s.l[4] | s.l[5] | s.l[6] | s.l[7];
+    if (rest == 0 && s.l[0] == 1) {                                  // Exponent::One, :246-252
+        if (A.mode == 1) A.ones_list[atomicAdd(A.ones_count, 1u)] = local;
+        return;
+    }
+    const uint32_t D = 1u << (A.c - 1);
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < A.W; w++) {
+        uint32_t raw = extract_bits(s.l, w * A.c, A.c) + carry;
+        uint32_t mag, neg;
+        if (raw > D) { mag = (1u << A.c) - raw; neg = 1; carry = 1; }
+        else { mag = raw; neg = 0; carry = 0; }
+        if (mag == 0) continue;
+        uint32_t key = w * D + (mag - 1);
+        if (A.mode == 0) atomicAdd(&A.counts[key], 1u);
+        else A.sorted[atomicAdd(&A.counts[key], 1u)] = local | (neg << 31);
+    }
+}
+
+// ---- exclusive scan over the histogram (NB+1 outputs) ---------------------------------
+constexpr int SCAN_ITEMS = 8, SCAN_THREADS = 256, SCAN_TILE = SCAN_ITEMS * SCAN_THREADS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t ws = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, ws, d);
+            if (lane >= d) ws += t;
+        }
+        if (lane < SCAN_THREADS / 32) warp_sums[lane] = ws;
+    }
+    __syncthreads();
+    uint32_t prefix = wid ? warp_sums[wid - 1] : 0;
+    *total = warp_sums[SCAN_THREADS / 32 - 1];
+    uint32_t res = prefix + inc - v;
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t* in, uint32_t* out, size_t n, uint32_t* tile_sums) {
+    size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = base + k < n ? in[base + k] : 0; sum += v[k]; }
+    uint32_t total, ex = block_exclusive_scan(sum, &total);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(uint32_t* tile_sums, size_t ntiles) {
+    uint32_t running = 0;
+    for (size_t base = 0; base < ntiles; base += SCAN_THREADS) {
+        size_t i = base + threadIdx.x;
+        uint32_t v = i < ntiles ? tile_sums[i] : 0;
+        uint32_t total, ex = block_exclusive_scan(v, &total);
+        if (i < ntiles) tile_sums[i] = running + ex;
+        running += total;
+    }
+}
+// out[i] += tile offset; also writes the grand total at out[n] and copies to cursor
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_finish(uint32_t* out, uint32_t* cursor, size_t n, const uint32_t* tile_sums,
+                                                              const uint32_t* in) {
+    size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t off = tile_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        size_t i = base + k;
+        if (i < n) {
+            uint32_t cnt = in[i];                 // `in` aliases `cursor`: read before the overwrite
+            uint32_t v = out[i] + off;
+            out[i] = v;
+            cursor[i] = v;
+            if (i == n - 1) out[n] = v + cnt;
+        }
+    }
+}
+
+// ---- bucket accumulation ------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ offsets,
+                                                        const uint32_t* __restrict__ sorted, XYZZ<F>* buckets, size_t nb,
+                                                        uint32_t* err) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    uint32_t start = offsets[b], end = offsets[b + 1];
+    XYZZ<F> acc = XYZZ<F>::identity();
+    for (uint32_t k = start; k < end; k++) {
+        uint32_t v = sorted[k];
+        Affine<F> p = ld_affine(bases + (v & 0x7fffffffu));
+        if (p.is_identity()) { err[1] = 1; continue; }               // Source::next, multiexp.rs:63-65
+        if (v >> 31) p.y = p.y.neg();
+        acc.add_mixed(p);
+    }
+    st_words(buckets + b, acc);
+}
+
+// sum of listed bases (scalar == 1): thread-strided partials then CTA tree
+template <class F>
+__device__ __forceinline__ void block_tree_reduce(XYZZ<F>& acc, XYZZ<F>* sh) {
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t stride = blockDim.x / 2; stride > 0; stride >>= 1) {
+        if (threadIdx.x < stride) {
+            XYZZ<F> a = sh[threadIdx.x];
+            a.add(sh[threadIdx.x + stride]);
+            sh[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    acc = sh[0];
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_sum_list(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ list,
+                                                      const uint32_t* __restrict__ count, XYZZ<F>* partials, uint32_t* err) {
+    extern __shared__ uint4 shraw[];
+    XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(shraw);
+    uint32_t n = *count;
+    XYZZ<F> acc = XYZZ<F>::identity();
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        Affine<F> p = ld_affine(bases + list[k]);
+        if (p.is_identity()) { err[1] = 1; continue; }
+        acc.add_mixed(p);
+    }
+    block_tree_reduce(acc, sh);
+    if (threadIdx.x == 0) st_words(partials + blockIdx.x, acc);
+}
+
+// out[g] = sum_{k < cnt} in[g*cnt + k]
+template <class F>
+__global__ void __launch_bounds__(128) k_point_tree_sum(const XYZZ<F>* in, uint32_t cnt, XYZZ<F>* out) {
+    extern __shared__ uint4 shraw[];
+    XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(shraw);
+    XYZZ<F> acc = XYZZ<F>::identity();
+    for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) acc.add(ld_words(in + (size_t)blockIdx.x * cnt + k));
+    block_tree_reduce(acc, sh);
+    if (threadIdx.x == 0) st_words(out + blockIdx.x, acc);
+}
+
+// Summation by parts (multiexp.rs:271-275) in parallel.  Window w = blockIdx.y; its D buckets
+// are cut into gridDim.x*blockDim.x runs of K; run j contributes
+//   sum_{t<K} (t+1) B[jK+t]  +  jK * sum_t B[jK+t].
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_reduce(const XYZZ<F>* buckets, uint32_t D, uint32_t K, XYZZ<F>* partials) {
+    extern __shared__ uint4 shraw[];
+    XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(shraw);
+    const uint32_t w = blockIdx.y;
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    XYZZ<F> acc = XYZZ<F>::identity();
+    if ((uint64_t)j * K < D) {
+        const XYZZ<F>* B = buckets + (size_t)w * D + (size_t)j * K;
+        XYZZ<F> running = XYZZ<F>::identity();
+        for (int t = (int)K - 1; t >= 0; t--) {
+            running.add(ld_words(B + t));
+            acc.add(running);
+        }
+        uint32_t m = j * K;                          // lift by the run's offset
+        if (m) {
+            XYZZ<F> lifted = XYZZ<F>::identity();
+            for (int bit = 31 - __clz(m); bit >= 0; bit--) {
+                lifted = lifted.dbl();
+                if ((m >> bit) & 1) lifted.add(running);
+            }
+            acc.add(lifted);
+        }
+    }
+    block_tree_reduce(acc, sh);
+    if (threadIdx.x == 0) st_words(partials + (size_t)w * gridDim.x + blockIdx.x, acc);
+}
+
+// Error classification when BOTH an EOF and an identity base were seen: the reference folds
+// window results from the top window down (multiexp.rs:295-300), so the error reported is the
+// top window's, and that window raises UnexpectedIdentity only for an identity base whose
+// digit *in that window* (window size c_ref = ceil(ln n), :318-322) is non-zero and that is
+// consumed before the bases run out.  Finds the first such scalar index.
+template <class F>
+__global__ void __launch_bounds__(256) k_msm_classify(DigitArgs A, const Affine<F>* bases, uint32_t c_ref, uint32_t top_chunk,
+                                                      uint32_t* first_top_identity) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    uint64_t rank = i;
+    if (A.density) {
+        uint64_t word = A.density[i >> 6];
+        if (!((word >> (i & 63)) & 1)) return;
+        rank = (uint64_t)A.density_rank[i >> 6] + __popcll(word & ((1ull << (i & 63)) - 1ull));
+    }
+    uint64_t gi = A.base_offset + rank;
+    if (gi >= A.global_len || gi < A.shard_lo || gi >= A.shard_lo + A.shard_n) return;
+    Fr s = *(A.scalars + i);
+    if (A.montgomery) s = fr_to_canonical(s);
+    if (s.is_zero()) return;
+    uint32_t rest = s.l[1] | s.l[2] | s.l[3] | s.l[4] | s.l[5] | s.l[6] | s.l[7];
+    bool one = rest == 0 && s.l[0] == 1;
+    bool hit = one ? (top_chunk == 0) : (extract_bits(s.l, top_chunk * c_ref, c_ref) != 0);
+    if (!hit) return;
+    Affine<F> p = ld_affine(bases + (gi - A.shard_lo));
+    if (p.is_identity()) atomicMin(first_top_identity, (uint32_t)i);
+}
+
+}  // namespace bb
+
+using namespace bb;
+
+// ----------------------------------------------------------------------------------------------
+struct bb_msm_job {
+    bb_ctx* ctx = nullptr;
+    const bb_bases* bases = nullptr;
+    cudaStream_t st = nullptr;
+    int group = BB_G1;
+    uint32_t c = 0, W = 0, D = 0;
+    size_t n = 0;
+    int status = BB_OK;              // pre-launch failure, reported at wait()
+    DigitArgs dargs{};
+    DevBuf d_scalars, d_density, d_rank, d_counts, d_offsets, d_tiles, d_sorted, d_buckets, d_partials, d_final, d_ones, d_err;
+    std::vector<uint32_t> h_rank;
+    void* h_out = nullptr;           // pinned: [W window sums][1 ones sum] then err[4]
+    size_t h_out_bytes = 0;
+};
+
+namespace {
+
+uint32_t choose_window(bb_ctx* ctx, size_t n) {
+    if (ctx->opt_msm_window_bits >= 2 && ctx->opt_msm_window_bits <= 24) return (uint32_t)ctx->opt_msm_window_bits;
+    if (n < 32) return 4;
+    // minimise  W * (n + 3 * 2^(c-1))  with W = 255/c + 1: accumulation adds + reduction adds
+    uint32_t best = 4;
+    double best_cost = 1e300;
+    for (uint32_t c = 4; c <= 22; c++) {
+        double W = 255 / c + 1;
+        double cost = W * ((double)n + 3.0 * (double)(1u << (c - 1)));
+        if (cost < best_cost) { best_cost = cost; best = c; }
+    }
+    return best;
+}
+
+template <class F>
+int launch_msm(bb_msm_job* job) {
+    bb_ctx* ctx = job->ctx;
+    cudaStream_t st = job->st;
+    const uint32_t W = job->W, D = job->D;
+    const size_t NB = (size_t)W * D;
+    const size_t n = job->n;
+    BB_TRY(job->d_counts.alloc(ctx, (NB + 1) * 4));
+    BB_TRY(job->d_offsets.alloc(ctx, (NB + 1) * 4));
+    size_t ntiles = (NB + SCAN_TILE - 1) / SCAN_TILE;
+    BB_TRY(job->d_tiles.alloc(ctx, ntiles * 4));
+    BB_TRY(job->d_sorted.alloc(ctx, (n ? n : 1) * (size_t)W * 4));
+    BB_TRY(job->d_ones.alloc(ctx, (n + 4) * 4));
+    BB_TRY(job->d_err.alloc(ctx, 16));
+    BB_TRY(job->d_buckets.alloc(ctx, NB * sizeof(XYZZ<F>)));
+    // reduction geometry: K buckets per thread, 128 threads per CTA
+    uint32_t K = 16;
+    while (K > 1 && (D / K) < 128) K >>= 1;
+    uint32_t runs = (D + K - 1) / K;
+    uint32_t nblk = (runs + 127) / 128;
+    const uint32_t ONES_BLOCKS = 64;
+    BB_TRY(job->d_partials.alloc(ctx, ((size_t)W * nblk + ONES_BLOCKS) * sizeof(XYZZ<F>)));
+    BB_TRY(job->d_final.alloc(ctx, (size_t)(W + 1) * sizeof(XYZZ<F>) + 16));
+
+    BB_CUDA(cudaMemsetAsync(job->d_counts.p, 0, (NB + 1) * 4, st));
+    BB_CUDA(cudaMemsetAsync(job->d_err.p, 0xff, 4, st));
+    BB_CUDA(cudaMemsetAsync((char*)job->d_err.p + 4, 0, 12, st));
+    BB_CUDA(cudaMemsetAsync(job->d_ones.p, 0, 4, st));
+
+    DigitArgs& A = job->dargs;
+    A.counts = job->d_counts.as<uint32_t>();
+    A.sorted = job->d_sorted.as<uint32_t>();
+    A.ones_count = job->d_ones.as<uint32_t>();
+    A.ones_list = job->d_ones.as<uint32_t>() + 4;
+    A.err = job->d_err.as<uint32_t>();
+    if (n) {
+        A.mode = 0;
+        k_msm_digits<<<cdiv(n, 256), 256, 0, st>>>(A);
+        ctx->count_launch();
+    }
+    uint32_t* offsets = job->d_offsets.as<uint32_t>();
+    k_scan_tiles<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(A.counts, offsets, NB, job->d_tiles.as<uint32_t>());
+    k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(job->d_tiles.as<uint32_t>(), ntiles);
+    // cursors live in the histogram buffer: after this kernel counts[] holds bucket starts
+    k_scan_finish<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(offsets, A.counts, NB, job->d_tiles.as<uint32_t>(), A.counts);
+    ctx->count_launch(3);
+    if (n) {
+        A.mode = 1;
+        k_msm_digits<<<cdiv(n, 256), 256, 0, st>>>(A);
+        ctx->count_launch();
+    }
+    const Affine<F>* bases = (const Affine<F>*)job->bases->d_points;
+    XYZZ<F>* buckets = job->d_buckets.as<XYZZ<F>>();
+    k_msm_accumulate<F><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, buckets, NB, A.err);
+    ctx->count_launch();
+    XYZZ<F>* partials = job->d_partials.as<XYZZ<F>>();
+    size_t sh = 128 * sizeof(XYZZ<F>);
+    if (sh > 48 * 1024) {
+        BB_CUDA(cudaFuncSetAttribute(k_msm_reduce<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        BB_CUDA(cudaFuncSetAttribute(k_msm_sum_list<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        BB_CUDA(cudaFuncSetAttribute(k_point_tree_sum<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    }
+    k_msm_reduce<F><<<dim3(nblk, W), 128, sh, st>>>(buckets, D, K, partials);
+    k_msm_sum_list<F><<<ONES_BLOCKS, 128, sh, st>>>(bases, A.ones_list, A.ones_count, partials + (size_t)W * nblk, A.err);
+    XYZZ<F>* fin = job->d_final.as<XYZZ<F>>();
+    k_point_tree_sum<F><<<W, 128, sh, st>>>(partials, nblk, fin);
+    k_point_tree_sum<F><<<1, 128, sh, st>>>(partials + (size_t)W * nblk, ONES_BLOCKS, fin + W);
+    ctx->count_launch(4);
+    BB_CUDA(cudaGetLastError());
+    size_t pts = (size_t)(W + 1) * sizeof(XYZZ<F>);
+    job->h_out_bytes = pts + 16;
+    BB_CUDA(cudaMallocHost(&job->h_out, job->h_out_bytes));
+    BB_CUDA(cudaMemcpyAsync(job->h_out, fin, pts, cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaMemcpyAsync((char*)job->h_out + pts, job->d_err.p, 16, cudaMemcpyDeviceToHost, st));
+    return BB_OK;
+}
+
+}  // namespace
+namespace bb {
+int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint64_t* density_bits, size_t density_len,
+              const void* scalars, bool scalars_on_device, size_t n, int form, cudaEvent_t wait_for, bb_msm_job** out) {
+    if (!ctx || !bases || !out || (n && !scalars)) { set_error("bb_msm: null argument"); return BB_ERR_ARG; }
+    if (n >= (1ull << 31) || bases->n >= (1ull << 31)) { set_error("bb_msm: more than 2^31 terms"); return BB_ERR_ARG; }
+    if (form != BB_FORM_CANONICAL && form != BB_FORM_MONTGOMERY) { set_error("bb_msm: bad form"); return BB_ERR_ARG; }
+    BB_CUDA(cudaSetDevice(ctx->device));
+    bb_msm_job* job = new bb_msm_job();
+    *out = job;
+    job->ctx = ctx; job->bases = bases; job->group = bases->group; job->n = n;
+    job->st = ctx->pick_stream();
+    if (wait_for) BB_CUDA(cudaStreamWaitEvent(job->st, wait_for, 0));
+    if (density_bits && density_len != n) {                 // the assert! at multiexp.rs:324-329
+        set_error("density map has %zu entries for %zu exponents", density_len, n);
+        job->status = BB_ERR_DENSITY_MISMATCH;
+        return BB_OK;
+    }
+    job->c = choose_window(ctx, n);
+    job->W = 255 / job->c + 1;
+    job->D = 1u << (job->c - 1);
+    auto fail = [&](int s) { job->status = s; return BB_OK; };
+    DigitArgs& A = job->dargs;
+    A.n = n; A.montgomery = form == BB_FORM_MONTGOMERY;
+    A.base_offset = base_offset;
+    A.shard_lo = bases->global_offset; A.shard_n = bases->n; A.global_len = bases->global_len;
+    A.c = job->c; A.W = job->W;
+    int s;
+    if (scalars_on_device) A.scalars = (const Fr*)scalars;
+    else {
+        if ((s = job->d_scalars.alloc(ctx, n * 32)) != BB_OK) return fail(s);
+        if (n && cudaMemcpyAsync(job->d_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, job->st) != cudaSuccess) {
+            set_error("scalar upload failed");
+            return fail(BB_ERR_CUDA);
+        }
+        A.scalars = job->d_scalars.as<Fr>();
+    }
+    if (density_bits) {
+        size_t words = (n + 63) / 64;
+        job->h_rank.resize(words ? words : 1);
+        uint32_t acc = 0;
+        for (size_t j = 0; j < words; j++) {
+            job->h_rank[j] = acc;
+            uint64_t wv = density_bits[j];
+            if (j == words - 1 && (n & 63)) wv &= (1ull << (n & 63)) - 1ull;
+            acc += (uint32_t)__builtin_popcountll(wv);
+        }
+        if ((s = job->d_density.alloc(ctx, words * 8)) != BB_OK) return fail(s);
+        if ((s = job->d_rank.alloc(ctx, words * 4)) != BB_OK) return fail(s);
+        if (words) {
+            cudaMemcpyAsync(job->d_density.p, density_bits, words * 8, cudaMemcpyHostToDevice, job->st);
+            cudaMemcpyAsync(job->d_rank.p, job->h_rank.data(), words * 4, cudaMemcpyHostToDevice, job->st);
+        }
+        A.density = job->d_density.as<uint64_t>();
+        A.density_rank = job->d_rank.as<uint32_t>();
+    }
+    s = job->group == BB_G1 ? launch_msm<Fp>(job) : launch_msm<Fp2>(job);
+    if (s != BB_OK) return fail(s);
+    return BB_OK;
+}
+
+}  // namespace bb
+namespace {
+// Horner fold over the window sums (multiexp.rs:295-300) plus the Exponent::One sum
+template <class F>
+XYZZ<F> fold_windows(const XYZZ<F>* win, uint32_t W, uint32_t c) {
+    XYZZ<F> acc = XYZZ<F>::identity();
+    for (int w = (int)W - 1; w >= 0; w--) {
+        for (uint32_t k = 0; k < c; k++) acc = acc.dbl();
+        acc.add(win[w]);
+    }
+    acc.add(win[W]);
+    return acc;
+}
+
+template <class F>
+int classify_both_errors(bb_msm_job* job, uint32_t eof_index, int* status) {
+    bb_ctx* ctx = job->ctx;
+    size_t n = job->n;
+    uint32_t c_ref = n < 32 ? 3u : (uint32_t)std::ceil(std::log((double)(uint32_t)n));   // multiexp.rs:318-322
+    uint32_t chunks = (255 + c_ref - 1) / c_ref;                                          // step_by(c) over 0..NUM_BITS
+    uint32_t* d_first = job->d_err.as<uint32_t>() + 2;
+    BB_CUDA(cudaMemsetAsync(d_first, 0xff, 4, job->st));
+    k_msm_classify<F><<<cdiv(n, 256), 256, 0, job->st>>>(job->dargs, (const Affine<F>*)job->bases->d_points, c_ref, chunks - 1, d_first);
+    ctx->count_launch();
+    uint32_t first = 0xffffffffu;
+    BB_CUDA(cudaMemcpyAsync(&first, d_first, 4, cudaMemcpyDeviceToHost, job->st));
+    BB_CUDA(cudaStreamSynchronize(job->st));
+    *status = first < eof_index ? BB_ERR_UNEXPECTED_IDENTITY : BB_ERR_IO_UNEXPECTED_EOF;
+    return BB_OK;
+}
+
+}  // namespace
+
+namespace bb {
+// used by prover.cu: wait and return the projective result
+int msm_wait_result(bb_msm_job* job, MsmResult* res) {
+    int status = job->status;
+    {   // also on a failed launch: kernels already queued may still use the job's buffers
+        cudaError_t e = cudaStreamSynchronize(job->st);
+        if (e != cudaSuccess && status == BB_OK) { set_error("msm stream: %s", cudaGetErrorString(e)); status = BB_ERR_CUDA; }
+    }
+    if (status == BB_OK) {
+        bool g2 = job->group == BB_G2;
+        size_t pts = (size_t)(job->W + 1) * (g2 ? sizeof(G2X) : sizeof(G1X));
+        const uint32_t* err = (const uint32_t*)((char*)job->h_out + pts);
+        bool eof = err[0] != 0xffffffffu, ident = err[1] != 0;
+        if (eof && ident) {
+            int s = g2 ? classify_both_errors<Fp2>(job, err[0], &status) : classify_both_errors<Fp>(job, err[0], &status);
+            if (s != BB_OK) status = s;
+        } else if (eof) {
+            status = BB_ERR_IO_UNEXPECTED_EOF;
+        } else if (ident) {
+            status = BB_ERR_UNEXPECTED_IDENTITY;
+        }
+        if (status == BB_ERR_IO_UNEXPECTED_EOF) set_error("expected more bases from source");
+        if (status == BB_ERR_UNEXPECTED_IDENTITY) set_error("encountered an identity element in the CRS");
+        if (status == BB_OK) {
+            res->g2 = g2;
+            if (g2) res->x2 = fold_windows<Fp2>((const G2X*)job->h_out, job->W, job->c);
+            else res->g1 = fold_windows<Fp>((const G1X*)job->h_out, job->W, job->c);
+        }
+    }
+    res->status = status;
+    if (job->h_out) cudaFreeHost(job->h_out);
+    delete job;
+    return status;
+}
+}  // namespace bb
+
+extern "C" {
+
+int bb_msm_async(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint64_t* density_bits, size_t density_len,
+                 const void* scalars, size_t n_scalars, int form, bb_msm_job** out) {
+    return msm_start(ctx, bases, base_offset, density_bits, density_len, scalars, false, n_scalars, form, nullptr, out);
+}
+int bb_msm_async_device(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint64_t* density_bits, size_t density_len,
+                        const void* d_scalars, size_t n_scalars, int form, bb_msm_job** out) {
+    return msm_start(ctx, bases, base_offset, density_bits, density_len, d_scalars, true, n_scalars, form, nullptr, out);
+}
+int bb_msm_wait(bb_msm_job* job, void* out_affine) {
+    if (!job || !out_affine) { set_error("bb_msm_wait: null argument"); return BB_ERR_ARG; }
+    MsmResult r;
+    int s = msm_wait_result(job, &r);
+    if (s != BB_OK) return s;
+    if (r.g2) { G2Affine a = r.x2.to_affine(); std::memcpy(out_affine, &a, sizeof a); }
+    else { G1Affine a = r.g1.to_affine(); std::memcpy(out_affine, &a, sizeof a); }
+    return BB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,239 @@
+// bellman_b200: the device side of groth16::create_proof after synthesis
+// (/root/reference/groth16/src/prover.rs:217-360): CRS residency, the H pipeline, the eight
+// multiexps in flight, and the host finalisation.
+#include "bb_internal.cuh"
+
+using namespace bb;
+
+struct bb_crs {
+    bb_ctx* ctx = nullptr;
+    bb_bases *h = nullptr, *l = nullptr, *a = nullptr, *b_g1 = nullptr, *b_g2 = nullptr;
+    G1Affine alpha_g1, beta_g1, delta_g1;
+    G2Affine beta_g2, delta_g2;
+    uint32_t shard_index = 0, shard_count = 1;
+};
+
+namespace {
+
+template <class F>
+bool affine_equal(const Affine<F>& a, const Affine<F>& b) { return a.x == b.x && a.y == b.y; }
+
+// scalar multiplication on the host (the five Affine * Fr of prover.rs:326-337 and the two
+// MulAssign<Fr> of :342,351); k is a canonical little-endian 256-bit integer
+template <class F>
+XYZZ<F> host_mul(const XYZZ<F>& p, const uint32_t* k) {
+    // 4-bit fixed window
+    XYZZ<F> tab[16];
+    tab[0] = XYZZ<F>::identity();
+    for (int i = 1; i < 16; i++) { tab[i] = tab[i - 1]; tab[i].add(p); }
+    XYZZ<F> acc = XYZZ<F>::identity();
+    for (int i = 63; i >= 0; i--) {
+        for (int d = 0; d < 4; d++) acc = acc.dbl();
+        uint32_t nib = (k[i / 8] >> (4 * (i % 8))) & 15u;
+        if (nib) acc.add(tab[nib]);
+    }
+    return acc;
+}
+
+void fp_to_be(const Fp& v, uint8_t* out) {
+    Fp c = fp_to_canonical(v);
+    for (int i = 0; i < 12; i++)
+        for (int b = 0; b < 4; b++) out[47 - (4 * i + b)] = (uint8_t)(c.l[i] >> (8 * b));
+}
+bool fp_lexi_larger(const Fp& v) {               // canonical(v) > (p-1)/2
+    static const uint32_t half[12] = {BBC_FP_HALF_LIST};
+    Fp c = fp_to_canonical(v);
+    for (int i = 11; i >= 0; i--) {
+        if (c.l[i] > half[i]) return true;
+        if (c.l[i] < half[i]) return false;
+    }
+    return false;
+}
+
+}  // namespace
+
+namespace bb {
+void g1_compress(const G1Affine& p, uint8_t* out) {
+    if (p.is_identity()) { std::memset(out, 0, 48); out[0] = 0xC0; return; }
+    fp_to_be(p.x, out);
+    out[0] |= 0x80;
+    if (fp_lexi_larger(p.y)) out[0] |= 0x20;
+}
+void g2_compress(const G2Affine& p, uint8_t* out) {
+    if (p.is_identity()) { std::memset(out, 0, 96); out[0] = 0xC0; return; }
+    fp_to_be(p.x.c1, out);
+    fp_to_be(p.x.c0, out + 48);
+    out[0] |= 0x80;
+    bool larger = p.y.c1.is_zero() ? fp_lexi_larger(p.y.c0) : fp_lexi_larger(p.y.c1);
+    if (larger) out[0] |= 0x20;
+}
+G1X g1_host_mul(const G1X& p, const uint32_t* k) { return host_mul<Fp>(p, k); }
+G2X g2_host_mul(const G2X& p, const uint32_t* k) { return host_mul<Fp2>(p, k); }
+}  // namespace bb
+
+extern "C" {
+
+int bb_crs_create(bb_ctx* ctx, const bb_crs_desc* d, bb_crs** out) {
+    if (!ctx || !d || !out) { set_error("bb_crs_create: null argument"); return BB_ERR_ARG; }
+    if (!d->alpha_g1 || !d->beta_g1 || !d->delta_g1 || !d->beta_g2 || !d->delta_g2) { set_error("bb_crs_create: missing vk element"); return BB_ERR_ARG; }
+    uint32_t cnt = d->shard_count ? d->shard_count : 1, idx = d->shard_index;
+    if (idx >= cnt) { set_error("bb_crs_create: shard %u of %u", idx, cnt); return BB_ERR_ARG; }
+    bb_crs* crs = new bb_crs();
+    crs->ctx = ctx; crs->shard_index = idx; crs->shard_count = cnt;
+    std::memcpy(&crs->alpha_g1, d->alpha_g1, 96); std::memcpy(&crs->beta_g1, d->beta_g1, 96);
+    std::memcpy(&crs->delta_g1, d->delta_g1, 96);
+    std::memcpy(&crs->beta_g2, d->beta_g2, 192); std::memcpy(&crs->delta_g2, d->delta_g2, 192);
+    auto up = [&](int group, const void* pts, size_t len, bb_bases** dst) -> int {
+        size_t lo = len * idx / cnt, hi = len * (idx + 1) / cnt;
+        size_t stride = group == BB_G1 ? 96 : 192;
+        return bb_bases_upload(ctx, group, (const char*)pts + lo * stride, hi - lo, lo, len, dst);
+    };
+    int s;
+    if ((s = up(BB_G1, d->h, d->h_len, &crs->h)) || (s = up(BB_G1, d->l, d->l_len, &crs->l)) ||
+        (s = up(BB_G1, d->a, d->a_len, &crs->a)) || (s = up(BB_G1, d->b_g1, d->b_g1_len, &crs->b_g1)) ||
+        (s = up(BB_G2, d->b_g2, d->b_g2_len, &crs->b_g2))) {
+        bb_crs_destroy(crs);
+        return s;
+    }
+    *out = crs;
+    return BB_OK;
+}
+
+void bb_crs_destroy(bb_crs* crs) {
+    if (!crs) return;
+    bb_bases_free(crs->h); bb_bases_free(crs->l); bb_bases_free(crs->a); bb_bases_free(crs->b_g1); bb_bases_free(crs->b_g2);
+    delete crs;
+}
+
+int bb_groth16_prove_partials(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, uint8_t* partials) {
+    if (!ctx || !crs || !w || !partials) { set_error("bb_groth16_prove_partials: null argument"); return BB_ERR_ARG; }
+    BB_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = w->n_constraints;
+    size_t m = 1;
+    uint32_t log_m = 0;
+    while (m < n) {                                   // from_coeffs, domain.rs:49-60
+        m *= 2;
+        log_m += 1;
+        if (log_m >= (uint32_t)bbc::FR_S) { set_error("PolynomialDegreeTooLarge"); return BB_ERR_POLYNOMIAL_DEGREE_TOO_LARGE; }
+    }
+    cudaStream_t st = ctx->main_stream;
+    DevBuf d_a, d_b, d_c, d_tmp, d_in, d_aux;
+    BB_TRY(d_a.alloc(ctx, m * 32)); BB_TRY(d_b.alloc(ctx, m * 32)); BB_TRY(d_c.alloc(ctx, m * 32)); BB_TRY(d_tmp.alloc(ctx, m * 32));
+    BB_TRY(d_in.alloc(ctx, w->n_inputs * 32)); BB_TRY(d_aux.alloc(ctx, w->n_aux * 32));
+    // witness MSMs first: they do not depend on the H pipeline (prover.rs starts them after
+    // h, but all eight are in flight before the first wait, :244-318)
+    cudaStream_t up = ctx->pick_stream();
+    if (w->n_inputs) BB_CUDA(cudaMemcpyAsync(d_in.p, w->input_assignment, w->n_inputs * 32, cudaMemcpyHostToDevice, up));
+    if (w->n_aux) BB_CUDA(cudaMemcpyAsync(d_aux.p, w->aux_assignment, w->n_aux * 32, cudaMemcpyHostToDevice, up));
+    cudaEvent_t ev_up, ev_h;
+    BB_CUDA(cudaEventCreateWithFlags(&ev_up, cudaEventDisableTiming));
+    BB_CUDA(cudaEventCreateWithFlags(&ev_h, cudaEventDisableTiming));
+    BB_CUDA(cudaEventRecord(ev_up, up));
+    size_t b_in_total = 0;                            // get_total_density, prover.rs:288-291
+    for (size_t j = 0; j < (w->n_inputs + 63) / 64; j++) {
+        uint64_t wv = w->b_input_density[j];
+        if (j == (w->n_inputs + 63) / 64 - 1 && (w->n_inputs & 63)) wv &= (1ull << (w->n_inputs & 63)) - 1ull;
+        b_in_total += (size_t)__builtin_popcountll(wv);
+    }
+    bb_msm_job* jobs[8] = {nullptr};
+    int s = BB_OK;
+    auto start = [&](int slot, const bb_bases* bases, size_t off, const uint64_t* dens, size_t dens_len, const void* d_sc, size_t cnt, cudaEvent_t ev) {
+        if (s == BB_OK) s = msm_start(ctx, bases, off, dens, dens_len, d_sc, true, cnt, BB_FORM_MONTGOMERY, ev, &jobs[slot]);
+    };
+    start(1, crs->l, 0, nullptr, 0, d_aux.p, w->n_aux, ev_up);                                              // :263-268
+    start(2, crs->a, 0, nullptr, 0, d_in.p, w->n_inputs, ev_up);                                            // :275-280
+    start(3, crs->a, w->n_inputs, w->a_aux_density, w->n_aux, d_aux.p, w->n_aux, ev_up);                    // :281-286
+    start(4, crs->b_g1, 0, w->b_input_density, w->n_inputs, d_in.p, w->n_inputs, ev_up);                    // :296-301
+    start(5, crs->b_g1, b_in_total, w->b_aux_density, w->n_aux, d_aux.p, w->n_aux, ev_up);                  // :302-307
+    start(6, crs->b_g2, 0, w->b_input_density, w->n_inputs, d_in.p, w->n_inputs, ev_up);                    // :312-317
+    start(7, crs->b_g2, b_in_total, w->b_aux_density, w->n_aux, d_aux.p, w->n_aux, ev_up);                  // :318
+    // H pipeline (prover.rs:221-240)
+    if (s == BB_OK) {
+        auto stage = [&](DevBuf& d, const void* src) -> int {
+            if (m > n) BB_CUDA(cudaMemsetAsync((char*)d.p + n * 32, 0, (m - n) * 32, st));   // coeffs.resize(m, zero), domain.rs:69
+            if (n) BB_CUDA(cudaMemcpyAsync(d.p, src, n * 32, cudaMemcpyHostToDevice, st));
+            return BB_OK;
+        };
+        if ((s = stage(d_a, w->a)) == BB_OK && (s = stage(d_b, w->b)) == BB_OK && (s = stage(d_c, w->c)) == BB_OK)
+            s = h_poly_device(ctx, st, d_a.as<Fr>(), d_b.as<Fr>(), d_c.as<Fr>(), d_tmp.as<Fr>(), log_m);
+        if (s == BB_OK) {
+            cudaEventRecord(ev_h, st);
+            start(0, crs->h, 0, nullptr, 0, d_a.p, m - 1, ev_h);                                            // :238-244
+        }
+    }
+    // wait() x8 (prover.rs:339-354); always drain every started job
+    size_t off = 0;
+    for (int k = 0; k < 8; k++) {
+        bool g2 = k >= 6;
+        if (jobs[k]) {
+            MsmResult r;
+            int sk = msm_wait_result(jobs[k], &r);
+            if (s == BB_OK && sk != BB_OK) s = sk;
+            if (sk == BB_OK) {
+                if (g2) { G2Affine a = r.x2.to_affine(); std::memcpy(partials + off, &a, 192); }
+                else { G1Affine a = r.g1.to_affine(); std::memcpy(partials + off, &a, 96); }
+            }
+        }
+        off += g2 ? 192 : 96;
+    }
+    cudaStreamSynchronize(st);
+    cudaStreamSynchronize(up);
+    cudaEventDestroy(ev_up);
+    cudaEventDestroy(ev_h);
+    return s;
+}
+
+int bb_groth16_finalize(const bb_crs* crs, const uint8_t* partials, size_t count, const uint8_t* r_bytes, const uint8_t* s_bytes,
+                        uint8_t* proof) {
+    if (!crs || !partials || !count || !r_bytes || !s_bytes || !proof) { set_error("bb_groth16_finalize: null argument"); return BB_ERR_ARG; }
+    if (crs->delta_g1.is_identity() || crs->delta_g2.is_identity()) {              // prover.rs:320-324
+        set_error("delta is the identity: subversion-CRS attack");
+        return BB_ERR_UNEXPECTED_IDENTITY;
+    }
+    G1X sum1[6];
+    G2X sum2[2];
+    for (auto& p : sum1) p = G1X::identity();
+    for (auto& p : sum2) p = G2X::identity();
+    for (size_t c = 0; c < count; c++) {
+        const uint8_t* base = partials + c * BB_PARTIALS_BYTES;
+        for (int k = 0; k < 6; k++) { G1Affine a; std::memcpy(&a, base + 96 * k, 96); sum1[k].add_mixed(a); }
+        for (int k = 0; k < 2; k++) { G2Affine a; std::memcpy(&a, base + 576 + 192 * k, 192); sum2[k].add_mixed(a); }
+    }
+    Fr r, s;
+    std::memcpy(r.l, r_bytes, 32);
+    std::memcpy(s.l, s_bytes, 32);
+    Fr rs = fr_to_canonical(fr_from_canonical(r) * fr_from_canonical(s));        // rs.mul_assign(&s), :332-333
+    G1X g_a = g1_host_mul(G1X::from_affine(crs->delta_g1), r.l);                  // :326-327
+    g_a.add_mixed(crs->alpha_g1);
+    G2X g_b = g2_host_mul(G2X::from_affine(crs->delta_g2), s.l);                  // :328-329
+    g_b.add_mixed(crs->beta_g2);
+    G1X g_c = g1_host_mul(G1X::from_affine(crs->delta_g1), rs.l);                 // :335-337
+    g_c.add(g1_host_mul(G1X::from_affine(crs->alpha_g1), s.l));
+    g_c.add(g1_host_mul(G1X::from_affine(crs->beta_g1), r.l));
+    G1X a_answer = sum1[2];                                                       // :339-343
+    a_answer.add(sum1[3]);
+    g_a.add(a_answer);
+    g_c.add(g1_host_mul(a_answer, s.l));
+    G1X b1_answer = sum1[4];                                                      // :345-354
+    b1_answer.add(sum1[5]);
+    G2X b2_answer = sum2[0];
+    b2_answer.add(sum2[1]);
+    g_b.add(b2_answer);
+    g_c.add(g1_host_mul(b1_answer, r.l));
+    g_c.add(sum1[0]);
+    g_c.add(sum1[1]);
+    g1_compress(g_a.to_affine(), proof);                                          // :356-360 + lib.rs:39-45
+    g2_compress(g_b.to_affine(), proof + 48);
+    g1_compress(g_c.to_affine(), proof + 144);
+    return BB_OK;
+}
+
+int bb_groth16_prove(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, const uint8_t* r, const uint8_t* s, uint8_t* proof) {
+    if (crs && crs->shard_count != 1) { set_error("bb_groth16_prove needs an unsharded CRS; use prove_partials + finalize"); return BB_ERR_ARG; }
+    uint8_t partials[BB_PARTIALS_BYTES];
+    std::memset(partials, 0, sizeof partials);
+    BB_TRY(bb_groth16_prove_partials(ctx, crs, w, partials));
+    return bb_groth16_finalize(crs, partials, 1, r, s, proof);
+}
+
+}  // extern "C"

@@ -1,0 +1,191 @@
+/*
+ * bellman_b200 -- C ABI of the B200-native Groth16 proving back-end for bellman.
+ *
+ * This is the drop-in boundary for the two hot paths behind groth16::create_proof
+ * (SURVEY.md 8b).  bellman has no FFI seam of its own; each entry point below
+ * cites the Rust item a thin shim would forward to it (paths relative to the
+ * bellman source tree), and INTEGRATION.md shows that shim.
+ *
+ * Plain pointers and sizes only.  All functions return a bb_status; no exception
+ * or abort crosses the boundary.  bb_last_error() gives a thread-local message.
+ *
+ * Data formats
+ *   Fr element   32 bytes, 4 x u64 little-endian limbs.
+ *                BB_FORM_MONTGOMERY: value * 2^256 mod r (bls12_381::Scalar's in-memory
+ *                form, what EvaluationDomain's Vec<Scalar<Fr>> holds);
+ *                BB_FORM_CANONICAL: the integer itself (PrimeField::to_repr /
+ *                PrimeFieldBits::to_le_bits, what Exponent::Bits holds,
+ *                src/multiexp.rs:166-182).
+ *   G1 affine    96 bytes: x | y, each 6 x u64 LE limbs, Montgomery (value * 2^384 mod p).
+ *   G2 affine    192 bytes: x.c0 | x.c1 | y.c0 | y.c1.
+ *                The identity is encoded as all-zero bytes ((0,0) is on neither curve).
+ *   density      bit i of word i/64 (LSB first) = "variable i appears in this query"
+ *                (bitvec::BitVec<usize, Lsb0> raw storage of DensityTracker,
+ *                src/multiexp.rs:118-157).  NULL = FullDensity (:97-116).
+ */
+#ifndef BELLMAN_B200_H
+#define BELLMAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum bb_status {
+    BB_OK = 0,
+    /* SynthesisError values that can originate on this path (src/lib.rs:304-319) */
+    BB_ERR_POLYNOMIAL_DEGREE_TOO_LARGE = 1, /* domain.rs:57-59 */
+    BB_ERR_UNEXPECTED_IDENTITY = 2,         /* multiexp.rs:63-65, prover.rs:320-324 */
+    BB_ERR_IO_UNEXPECTED_EOF = 3,           /* multiexp.rs:55-61,74-80 */
+    BB_ERR_DENSITY_MISMATCH = 5,            /* the assert! at multiexp.rs:324-329 (a panic upstream) */
+    /* back-end errors */
+    BB_ERR_ARG = 16,
+    BB_ERR_CUDA = 17,
+    BB_ERR_NO_DEVICE = 18,
+    BB_ERR_OOM = 19
+} bb_status;
+
+typedef enum bb_form { BB_FORM_CANONICAL = 0, BB_FORM_MONTGOMERY = 1 } bb_form;
+
+/* EvaluationDomain methods, src/domain.rs:81-125 */
+typedef enum bb_ntt_mode { BB_NTT_FFT = 0, BB_NTT_IFFT = 1, BB_NTT_COSET_FFT = 2, BB_NTT_ICOSET_FFT = 3 } bb_ntt_mode;
+
+typedef enum bb_group { BB_G1 = 1, BB_G2 = 2 } bb_group;
+
+typedef struct bb_ctx bb_ctx;         /* one CUDA device; stands where multicore::Worker stands (src/multicore.rs:21-92) */
+typedef struct bb_bases bb_bases;     /* device-resident Arc<Vec<G::Affine>> (groth16/src/lib.rs:227-243) */
+typedef struct bb_msm_job bb_msm_job; /* Waiter<Result<G, SynthesisError>> (src/multicore.rs:94-118) */
+typedef struct bb_crs bb_crs;         /* device-resident groth16::Parameters (groth16/src/lib.rs:222-244) */
+
+const char* bb_last_error(void);
+int bb_version(void);
+
+/* ---- context ------------------------------------------------------------------------ */
+/* Worker::new() (src/multicore.rs:24-27).  `device` is a CUDA ordinal.  Fails with
+ * BB_ERR_NO_DEVICE when no CUDA device is usable: there is no CPU fallback. */
+int bb_ctx_create(int device, bb_ctx** out);
+void bb_ctx_destroy(bb_ctx* ctx);
+/* tuning knobs; results never depend on them.  Known keys: "msm_window_bits" (0 = auto),
+ * "ntt_tile_log" , "ntt_col_bits". */
+int bb_ctx_set_option(bb_ctx* ctx, const char* key, long value);
+int bb_ctx_synchronize(bb_ctx* ctx);
+/* counters for the harness: number of kernels this context has launched */
+uint64_t bb_ctx_kernel_launches(const bb_ctx* ctx);
+
+/* device buffers, so a caller can keep inputs resident across calls (bench "value" leg) */
+int bb_device_alloc(bb_ctx* ctx, size_t bytes, void** d_out);
+int bb_device_free(bb_ctx* ctx, void* d_ptr);
+int bb_device_upload(bb_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int bb_device_download(bb_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+
+/* ---- NTT: EvaluationDomain::{fft, ifft, coset_fft, icoset_fft} (src/domain.rs:81-125),
+ *      i.e. best_fft (:261-269) plus the fused scale / distribute_powers passes --------- */
+/* In place on a host buffer of 2^log_n Fr elements.  log_n >= 32 (= Fr::S) returns
+ * BB_ERR_POLYNOMIAL_DEGREE_TOO_LARGE like from_coeffs (:55-59). */
+int bb_ntt(bb_ctx* ctx, void* fr_inout, uint32_t log_n, int mode, int form);
+/* same, on a device buffer (Montgomery form) */
+int bb_ntt_device(bb_ctx* ctx, void* d_fr_inout, uint32_t log_n, int mode);
+
+/* The H-polynomial block of create_proof (groth16/src/prover.rs:221-240): from_coeffs on
+ * a,b,c (pads to m = 2^k >= n), 3x ifft, 3x coset_fft, mul_assign, sub_assign,
+ * divide_by_z_on_coset, icoset_fft, truncate to m-1 coefficients.
+ * a,b,c: n_constraints Fr each (Montgomery, host).  h_out: room for m-1 Fr, canonical
+ * integers (the Exponent::Bits form multiexp consumes, prover.rs:242).  *m_out = m. */
+int bb_h_poly(bb_ctx* ctx, const void* a, const void* b, const void* c, size_t n_constraints,
+              void* h_out, size_t* m_out);
+
+/* ---- bases ---------------------------------------------------------------------------- */
+/* Uploads n affine points.  `global_offset`/`global_len` describe a shard of a larger base
+ * vector for multi-GPU runs (the shard holds indices [global_offset, global_offset+n) of a
+ * vector of global_len points); single-GPU callers pass 0 and n. */
+int bb_bases_upload(bb_ctx* ctx, int group, const void* affine, size_t n, size_t global_offset,
+                    size_t global_len, bb_bases** out);
+void bb_bases_free(bb_bases* b);
+
+/* ---- MSM: multiexp() (src/multiexp.rs:305-332) ---------------------------------------- */
+/* Sum over i with density bit set of scalars[i] * bases[base_offset + rank(i)], where rank(i)
+ * counts set density bits below i (bases are compacted to set bits, App. C.3).
+ * Semantics preserved from multiexp_inner (:242-265): a zero scalar skips its base even if
+ * that base is the identity; an identity base under a non-zero scalar is
+ * BB_ERR_UNEXPECTED_IDENTITY; running out of bases is BB_ERR_IO_UNEXPECTED_EOF; a density of
+ * the wrong length is BB_ERR_DENSITY_MISMATCH.  Returns immediately; the job runs on its own
+ * CUDA stream (prover.rs:244-318 starts 8 of these before the first wait()).
+ * Host buffers must stay valid until bb_msm_wait returns. */
+int bb_msm_async(bb_ctx* ctx, const bb_bases* bases, size_t base_offset,
+                 const uint64_t* density_bits, size_t density_len,
+                 const void* scalars, size_t n_scalars, int form, bb_msm_job** out);
+/* scalars already in HBM (canonical or Montgomery per `form`) */
+int bb_msm_async_device(bb_ctx* ctx, const bb_bases* bases, size_t base_offset,
+                        const uint64_t* density_bits, size_t density_len,
+                        const void* d_scalars, size_t n_scalars, int form, bb_msm_job** out);
+/* Waiter::wait() (src/multicore.rs:98-108).  Writes the result as an affine point in the
+ * format above (G1 96 B / G2 192 B), frees the job.  With a sharded `bases` the result is
+ * this shard's partial sum. */
+int bb_msm_wait(bb_msm_job* job, void* out_affine);
+
+/* small group helpers for the host side of a multi-GPU reduction (affine in/out) */
+int bb_point_add(int group, const void* a_affine, const void* b_affine, void* out_affine);
+int bb_point_mul(int group, const void* a_affine, const void* fr_scalar, int form, void* out_affine);
+/* GroupEncoding::to_bytes: G1 48 B / G2 96 B compressed ZCash encoding */
+int bb_point_compress(int group, const void* affine, uint8_t* out);
+/* out[i] = [k_i] * generator, computed on the device (fixed-base); used to manufacture
+ * synthetic CRS material of benchmark size (generator.rs:271-296,398-415 equivalent). */
+int bb_fixed_base_mul(bb_ctx* ctx, int group, const void* fr_scalars, size_t n, int form, void* out_affine);
+
+/* ---- whole prover: create_proof after synthesis (groth16/src/prover.rs:217-360) -------- */
+typedef struct bb_crs_desc {
+    /* VerifyingKey parts the prover reads (prover.rs:219,320-337) */
+    const void* alpha_g1; const void* beta_g1; const void* delta_g1;   /* 96 B each  */
+    const void* beta_g2;  const void* delta_g2;                        /* 192 B each */
+    /* Parameters vectors (groth16/src/lib.rs:227-243) */
+    const void* h;    size_t h_len;
+    const void* l;    size_t l_len;
+    const void* a;    size_t a_len;
+    const void* b_g1; size_t b_g1_len;
+    const void* b_g2; size_t b_g2_len;
+    /* multi-GPU: this process holds shard `shard_index` of `shard_count` contiguous base
+     * ranges of every vector above (the arrays passed are still the full vectors; the
+     * library uploads only its range).  Single GPU: 0 / 1. */
+    uint32_t shard_index; uint32_t shard_count;
+} bb_crs_desc;
+
+int bb_crs_create(bb_ctx* ctx, const bb_crs_desc* desc, bb_crs** out);
+void bb_crs_destroy(bb_crs* crs);
+
+/* What ProvingAssignment holds when synthesis is done (prover.rs:57-71,193-215), i.e.
+ * including the trailing "input * 0 = 0" constraints. */
+typedef struct bb_witness {
+    const void* a; const void* b; const void* c; size_t n_constraints;   /* Fr, Montgomery */
+    const void* input_assignment; size_t n_inputs;                        /* Fr, Montgomery */
+    const void* aux_assignment;   size_t n_aux;                           /* Fr, Montgomery */
+    const uint64_t* a_aux_density;   /* n_aux bits   */
+    const uint64_t* b_input_density; /* n_inputs bits */
+    const uint64_t* b_aux_density;   /* n_aux bits   */
+} bb_witness;
+
+/* Eight partial MSM results of one proof, in the order prover.rs starts them:
+ * h, l, a_inputs, a_aux, b_g1_inputs, b_g1_aux (G1, 96 B each) then b_g2_inputs, b_g2_aux
+ * (G2, 192 B each): 6*96 + 2*192 = 960 bytes. */
+#define BB_PARTIALS_BYTES 960
+/* NTT pipeline + the 8 MSMs over this context's CRS shard. */
+int bb_groth16_prove_partials(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, uint8_t partials[BB_PARTIALS_BYTES]);
+/* Sums `count` partial sets (one per shard) and applies prover.rs:320-360 + Proof::write
+ * (groth16/src/lib.rs:39-45).  r, s: 32-byte canonical little-endian scalars. */
+int bb_groth16_finalize(const bb_crs* crs, const uint8_t* partials, size_t count,
+                        const uint8_t r[32], const uint8_t s[32], uint8_t proof[192]);
+/* single-GPU convenience: partials + finalize */
+int bb_groth16_prove(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w,
+                     const uint8_t r[32], const uint8_t s[32], uint8_t proof[192]);
+
+/* ---- diagnostics (used by the parity tests; not part of the bellman-facing surface) ------ */
+/* element-wise on the device: field 0 = Fr, 1 = Fp (Montgomery); op 0 mul, 1 add, 2 sub, 3 sqr */
+int bb_selftest_field(bb_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n);
+/* element-wise on affine points: op 0: a + b (mixed add); 1: 2a + b; 2: a + (2b - b) */
+int bb_selftest_point(bb_ctx* ctx, int group, int op, const void* a, const void* b, void* out, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BELLMAN_B200_H */

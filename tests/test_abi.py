@@ -1,0 +1,55 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/bellman_b200.h declares, and refuses to run without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import bellman_b200 as bb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "bellman_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_is_built_in_tree():
+    assert os.path.exists(bb.LIB_PATH), "run __graft_entry__.build() first"
+    assert os.path.dirname(bb.LIB_PATH) == os.path.join(ROOT, "bellman_b200")
+
+
+def test_every_declared_symbol_is_exported():
+    lib = bb.load_library()
+    names = declared_symbols()
+    assert len(names) >= 25
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/bellman_b200.h but not exported"
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(bb.BackendError) as ei:
+        bb.Worker()
+    assert "no CPU fallback" in str(ei.value) or "18" in str(ei.value)
+
+
+def test_density_packing_matches_bitvec_lsb0():
+    words, n = bb.pack_density([1, 0, 0, 1] + [0] * 60 + [1])
+    assert n == 65 and int(words[0]) == 0b1001 and int(words[1]) == 1
+    words, n = bb.pack_density([])
+    assert n == 0 and words.shape[0] >= 1
+
+
+def test_product_does_not_reference_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py may touch oracle/."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "bellman_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in src.lower() or f == "__init__.py" and "oracle" not in src, (dirpath, f)
