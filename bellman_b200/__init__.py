@@ -131,6 +131,19 @@ class Worker:
     def kernel_launches(self):
         return int(load_library().bb_ctx_kernel_launches(self._h))
 
+    def profile_read(self, what):
+        ms, launches, units = C.c_double(), C.c_uint64(), C.c_uint64()
+        _check(load_library().bb_profile_read(self._h, what.encode(), C.byref(ms), C.byref(launches), C.byref(units)))
+        return ms.value, launches.value, units.value
+
+    def profile_reset(self):
+        _check(load_library().bb_profile_reset(self._h))
+
+    def bytes_copied(self):
+        h2d, d2h = C.c_uint64(), C.c_uint64()
+        _check(load_library().bb_ctx_bytes_copied(self._h, C.byref(h2d), C.byref(d2h)))
+        return h2d.value, d2h.value
+
     # raw device buffers (bench: inputs resident in HBM before the timed region)
     def device_alloc(self, nbytes):
         p = C.c_void_p()
@@ -334,7 +347,8 @@ class _Witness(C.Structure):
     _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p), ("n_constraints", C.c_size_t),
                 ("input_assignment", C.c_void_p), ("n_inputs", C.c_size_t),
                 ("aux_assignment", C.c_void_p), ("n_aux", C.c_size_t),
-                ("a_aux_density", C.c_void_p), ("b_input_density", C.c_void_p), ("b_aux_density", C.c_void_p)]
+                ("a_aux_density", C.c_void_p), ("b_input_density", C.c_void_p), ("b_aux_density", C.c_void_p),
+                ("on_device", C.c_int)]
 
 
 class Parameters:
@@ -383,8 +397,19 @@ class ProvingAssignment:
         self.b_input_density, _ = pack_density(b_input_density)
         self.b_aux_density, _ = pack_density(b_aux_density)
 
-    def _struct(self):
+    def _struct(self, device_ptrs=None):
+        """device_ptrs: optional dict a,b,c,inputs,aux -> device addresses (inputs resident in HBM)"""
         w = _Witness()
+        if device_ptrs is not None:
+            w.a, w.b, w.c = device_ptrs["a"], device_ptrs["b"], device_ptrs["c"]
+            w.n_constraints = self.a.shape[0]
+            w.input_assignment, w.n_inputs = device_ptrs["inputs"], self.input_assignment.shape[0]
+            w.aux_assignment, w.n_aux = device_ptrs["aux"], self.aux_assignment.shape[0]
+            w.a_aux_density = self.a_aux_density.ctypes.data
+            w.b_input_density = self.b_input_density.ctypes.data
+            w.b_aux_density = self.b_aux_density.ctypes.data
+            w.on_device = 1
+            return w
         w.a, w.b, w.c = self.a.ctypes.data, self.b.ctypes.data, self.c.ctypes.data
         w.n_constraints = self.a.shape[0]
         w.input_assignment, w.n_inputs = self.input_assignment.ctypes.data, self.input_assignment.shape[0]
@@ -399,10 +424,10 @@ def _scalar_bytes(v):
     return (C.c_uint8 * 32).from_buffer_copy(int(v).to_bytes(32, "little"))
 
 
-def prove_partials(assignment, params):
+def prove_partials(assignment, params, device_ptrs=None):
     """NTT pipeline + the eight MSMs over this process's CRS shard -> 960 bytes of partial sums."""
     out = (C.c_uint8 * PARTIALS_BYTES)()
-    w = assignment._struct()
+    w = assignment._struct(device_ptrs)
     _check(load_library().bb_groth16_prove_partials(params.worker._h, params._h, C.byref(w), out))
     return bytes(out)
 
@@ -416,10 +441,44 @@ def finalize(params, partial_sets, r, s):
     return bytes(proof)
 
 
-def create_proof(assignment, params, r, s):
+def create_proof(assignment, params, r, s, device_ptrs=None):
     """groth16::create_proof after synthesis (prover.rs:217-360) + Proof::write: 192 bytes.
     r, s are Python integers in [0, r)."""
     proof = (C.c_uint8 * 192)()
-    w = assignment._struct()
+    w = assignment._struct(device_ptrs)
     _check(load_library().bb_groth16_prove(params.worker._h, params._h, C.byref(w), _scalar_bytes(r), _scalar_bytes(s), proof))
     return bytes(proof)
+
+
+def synth_mimc(rounds, seed, pinned=False):
+    """bench-only: the MiMC-chain witness of `rounds` rounds as a ProvingAssignment (product-side
+    generator, bellman_b200/csrc/synth.cu).  pinned=True places the arrays in page-locked host
+    memory (torch) so that cudaMemcpyAsync runs at full PCIe speed."""
+    lib = load_library()
+    shape = np.zeros(7, np.uint64)
+    _check(lib.bb_synth_mimc_shape(C.c_size_t(rounds), _ptr(shape)))
+    ni, na, n = int(shape[0]), int(shape[1]), int(shape[2])
+
+    def buf(rows):
+        if pinned:
+            import torch
+            t = torch.zeros((rows, 4), dtype=torch.int64).pin_memory()
+            return t, t.numpy().view(np.uint64)
+        return None, np.zeros((rows, 4), np.uint64)
+
+    keep, arrs = [], []
+    for rows in (n, n, n, ni, na):
+        t, a = buf(rows)
+        keep.append(t)
+        arrs.append(a)
+    a, b, c, inputs, aux = arrs
+    words = (na + 63) // 64
+    ad, bd, bi = np.zeros(words, np.uint64), np.zeros(words, np.uint64), np.zeros(1, np.uint64)
+    _check(lib.bb_synth_mimc_witness(C.c_size_t(rounds), C.c_uint64(seed), _ptr(a), _ptr(b), _ptr(c), _ptr(inputs), _ptr(aux),
+                                     _ptr(ad), _ptr(bi), _ptr(bd)))
+    asg = ProvingAssignment.__new__(ProvingAssignment)
+    asg.a, asg.b, asg.c, asg.input_assignment, asg.aux_assignment = a, b, c, inputs, aux
+    asg.a_aux_density, asg.b_input_density, asg.b_aux_density = ad, bi, bd
+    asg._keep = keep
+    return asg, dict(num_inputs=ni, num_aux=na, num_constraints=n, m=int(shape[3]), a_aux_total=int(shape[4]),
+                     b_in_total=int(shape[5]), b_aux_total=int(shape[6]))

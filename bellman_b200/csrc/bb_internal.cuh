@@ -48,9 +48,18 @@ struct bb_ctx {
     size_t next_stream = 0;
     cudaStream_t main_stream = nullptr;
     std::atomic<uint64_t> launches{0};
+    std::atomic<uint64_t> h2d_bytes{0}, d2h_bytes{0};   // host<->device traffic of the hot-path calls
     long opt_msm_window_bits = 0;
     long opt_ntt_tile_log = 11;
     long opt_ntt_col_bits = 3;
+    long opt_profile = 0;
+    struct ProfEntry { double ms = 0; uint64_t launches = 0, units = 0; };
+    std::map<std::string, ProfEntry> prof;
+    void prof_add(const char* what, double ms, uint64_t launches, uint64_t units) {
+        std::lock_guard<std::mutex> g(mu);
+        ProfEntry& e = prof[what];
+        e.ms += ms; e.launches += launches; e.units += units;
+    }
     std::map<uint32_t, bb::NttTables*> ntt_tables;   // by log_n
 
     int alloc(size_t bytes, void** out);

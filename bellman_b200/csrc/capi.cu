@@ -226,6 +226,7 @@ int bb_ctx_set_option(bb_ctx* ctx, const char* key, long value) {
     if (k == "msm_window_bits") ctx->opt_msm_window_bits = value;
     else if (k == "ntt_tile_log") ctx->opt_ntt_tile_log = value;
     else if (k == "ntt_col_bits") ctx->opt_ntt_col_bits = value;
+    else if (k == "profile") ctx->opt_profile = value;
     else { set_error("unknown option %s", key); return BB_ERR_ARG; }
     return BB_OK;
 }
@@ -238,6 +239,30 @@ int bb_ctx_synchronize(bb_ctx* ctx) {
 }
 
 uint64_t bb_ctx_kernel_launches(const bb_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+int bb_profile_read(bb_ctx* ctx, const char* what, double* ms, uint64_t* launches, uint64_t* units) {
+    if (!ctx || !what) return BB_ERR_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    auto it = ctx->prof.find(what);
+    bb_ctx::ProfEntry e;
+    if (it != ctx->prof.end()) e = it->second;
+    if (ms) *ms = e.ms;
+    if (launches) *launches = e.launches;
+    if (units) *units = e.units;
+    return BB_OK;
+}
+int bb_ctx_bytes_copied(const bb_ctx* ctx, uint64_t* h2d, uint64_t* d2h) {
+    if (!ctx) return BB_ERR_ARG;
+    if (h2d) *h2d = ctx->h2d_bytes.load();
+    if (d2h) *d2h = ctx->d2h_bytes.load();
+    return BB_OK;
+}
+int bb_profile_reset(bb_ctx* ctx) {
+    if (!ctx) return BB_ERR_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->prof.clear();
+    return BB_OK;
+}
 
 int bb_device_alloc(bb_ctx* ctx, size_t bytes, void** d_out) {
     if (!ctx || !d_out) return BB_ERR_ARG;

@@ -34,7 +34,7 @@ struct XYZZ {
     }
 
     // 2*(x,y) for an affine input (dbl-2008-s-1 with ZZ = ZZZ = 1)
-    BB_HD_NOINLINE static XYZZ dbl_affine(const Affine<F>& a) {
+    BB_HD static XYZZ dbl_affine_impl(const Affine<F>& a) {
         F U = a.y.dbl();
         if (U.is_zero()) return identity();
         F V = U.sqr(), W = U * V, S = a.x * V;
@@ -47,7 +47,7 @@ struct XYZZ {
         r.ZZZ = W;
         return r;
     }
-    BB_HD_NOINLINE XYZZ dbl() const {                    // dbl-2008-s-1
+    BB_HD XYZZ dbl_impl() const {                        // dbl-2008-s-1
         if (is_identity()) return *this;
         F U = Y.dbl();
         F V = U.sqr(), W = U * V, S = X * V;
@@ -79,7 +79,7 @@ struct XYZZ {
         ZZZ = ZZZ * PPP;
     }
     // this += o  (add-2008-s)
-    BB_HD_NOINLINE void add(const XYZZ& o) {
+    BB_HD void add_impl(const XYZZ& o) {
         if (o.is_identity()) return;
         if (is_identity()) { *this = o; return; }
         F U1 = X * o.ZZ, U2 = o.X * ZZ;
@@ -98,6 +98,14 @@ struct XYZZ {
         ZZZ = ZZZ * o.ZZZ * PPP;
     }
     BB_HD XYZZ neg() const { return {X, Y.neg(), ZZ, ZZZ}; }
+
+    // Out-of-line entry points.  On the device the heavy point operations are real function
+    // calls (see BB_HD_NOINLINE in mp.cuh) taking and returning the points BY VALUE: handing
+    // the address of a kernel-local point to a non-inlined member function made nvcc 12.9
+    // drop a 16-byte store of that local afterwards (k_msm_reduce, seen in PTX and SASS).
+    BB_HD XYZZ dbl() const;
+    BB_HD void add(const XYZZ& o);
+    BB_HD static XYZZ dbl_affine(const Affine<F>& a);
 
     // x = X/ZZ, y = Y/ZZZ
     BB_HD Affine<F> to_affine() const {
@@ -118,6 +126,13 @@ struct XYZZ {
         return acc;
     }
 };
+
+template <class F> BB_HD_NOINLINE XYZZ<F> xyzz_dbl_outlined(XYZZ<F> a) { return a.dbl_impl(); }
+template <class F> BB_HD_NOINLINE XYZZ<F> xyzz_add_outlined(XYZZ<F> a, XYZZ<F> b) { a.add_impl(b); return a; }
+template <class F> BB_HD_NOINLINE XYZZ<F> xyzz_dbl_affine_outlined(Affine<F> a) { return XYZZ<F>::dbl_affine_impl(a); }
+template <class F> BB_HD XYZZ<F> XYZZ<F>::dbl() const { return xyzz_dbl_outlined<F>(*this); }
+template <class F> BB_HD void XYZZ<F>::add(const XYZZ<F>& o) { *this = xyzz_add_outlined<F>(*this, o); }
+template <class F> BB_HD XYZZ<F> XYZZ<F>::dbl_affine(const Affine<F>& a) { return xyzz_dbl_affine_outlined<F>(a); }
 
 typedef Affine<Fp> G1Affine;
 typedef Affine<Fp2> G2Affine;

@@ -58,14 +58,14 @@ BB_HD Fr fr_from_u64(uint64_t v) { Fr r = Fr::zero(); r.l[0] = (uint32_t)v; r.l[
 // a^(q-2)
 BB_HD Fr fr_inv(const Fr& a) {
     uint32_t e[8];
-    for (int i = 0; i < 8; i++) e[i] = Fr::modl(i);
-    e[0] -= 2;
+    uint32_t borrow = 2;                       // r - 2 (the low 32-bit limb of r is 1: borrows)
+    for (int i = 0; i < 8; i++) { uint32_t m = Fr::modl(i); e[i] = m - borrow; borrow = m < borrow ? 1u : 0u; }
     return a.pow(e, 8, fr_one());
 }
 BB_HD Fp fp_inv(const Fp& a) {
     uint32_t e[12];
-    for (int i = 0; i < 12; i++) e[i] = Fp::modl(i);
-    e[0] -= 2;
+    uint32_t borrow = 2;
+    for (int i = 0; i < 12; i++) { uint32_t m = Fp::modl(i); e[i] = m - borrow; borrow = m < borrow ? 1u : 0u; }
     return a.pow(e, 12, fp_one());
 }
 

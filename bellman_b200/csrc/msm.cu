@@ -22,6 +22,7 @@
 // reference's fast paths, kept because real witnesses are dominated by 0/1.
 // Error semantics (Source::next / skip, :53-86) are reproduced, see bb_msm_wait.
 #include <cmath>
+#include <cstdlib>
 
 #include "bb_internal.cuh"
 
@@ -225,17 +226,20 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const Affine<F>* __restr
 // sum of listed bases (scalar == 1): thread-strided partials then CTA tree
 template <class F>
 __device__ __forceinline__ void block_tree_reduce(XYZZ<F>& acc, XYZZ<F>* sh) {
-    sh[threadIdx.x] = acc;
+    // explicit 16-byte word copies (st_words / ld_words) rather than struct assignment: nvcc
+    // 12.9 drops the first 16-byte store of `sh[tid] = acc` in k_msm_reduce (seen in SASS)
+    st_words(sh + threadIdx.x, acc);
     __syncthreads();
     for (uint32_t stride = blockDim.x / 2; stride > 0; stride >>= 1) {
         if (threadIdx.x < stride) {
-            XYZZ<F> a = sh[threadIdx.x];
-            a.add(sh[threadIdx.x + stride]);
-            sh[threadIdx.x] = a;
+            XYZZ<F> a = ld_words(sh + threadIdx.x);
+            XYZZ<F> b = ld_words(sh + threadIdx.x + stride);
+            a.add(b);
+            st_words(sh + threadIdx.x, a);
         }
         __syncthreads();
     }
-    acc = sh[0];
+    acc = ld_words(sh);
 }
 
 template <class F>
@@ -343,6 +347,7 @@ struct bb_msm_job {
     std::vector<uint32_t> h_rank;
     void* h_out = nullptr;           // pinned: [W window sums][1 ones sum] then err[4]
     size_t h_out_bytes = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // profile: job start, accumulate start/end, job end
 };
 
 namespace {
@@ -390,6 +395,11 @@ int launch_msm(bb_msm_job* job) {
     BB_CUDA(cudaMemsetAsync((char*)job->d_err.p + 4, 0, 12, st));
     BB_CUDA(cudaMemsetAsync(job->d_ones.p, 0, 4, st));
 
+    const bool prof = ctx->opt_profile != 0;
+    if (prof) {
+        for (auto& e : job->ev) BB_CUDA(cudaEventCreate(&e));
+        BB_CUDA(cudaEventRecord(job->ev[0], st));
+    }
     DigitArgs& A = job->dargs;
     A.counts = job->d_counts.as<uint32_t>();
     A.sorted = job->d_sorted.as<uint32_t>();
@@ -414,8 +424,10 @@ int launch_msm(bb_msm_job* job) {
     }
     const Affine<F>* bases = (const Affine<F>*)job->bases->d_points;
     XYZZ<F>* buckets = job->d_buckets.as<XYZZ<F>>();
+    if (prof) BB_CUDA(cudaEventRecord(job->ev[1], st));
     k_msm_accumulate<F><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, buckets, NB, A.err);
     ctx->count_launch();
+    if (prof) BB_CUDA(cudaEventRecord(job->ev[2], st));
     XYZZ<F>* partials = job->d_partials.as<XYZZ<F>>();
     size_t sh = 128 * sizeof(XYZZ<F>);
     if (sh > 48 * 1024) {
@@ -435,6 +447,8 @@ int launch_msm(bb_msm_job* job) {
     BB_CUDA(cudaMallocHost(&job->h_out, job->h_out_bytes));
     BB_CUDA(cudaMemcpyAsync(job->h_out, fin, pts, cudaMemcpyDeviceToHost, st));
     BB_CUDA(cudaMemcpyAsync((char*)job->h_out + pts, job->d_err.p, 16, cudaMemcpyDeviceToHost, st));
+    ctx->d2h_bytes += pts + 16;
+    if (prof) BB_CUDA(cudaEventRecord(job->ev[3], st));
     return BB_OK;
 }
 
@@ -469,6 +483,7 @@ int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint
     if (scalars_on_device) A.scalars = (const Fr*)scalars;
     else {
         if ((s = job->d_scalars.alloc(ctx, n * 32)) != BB_OK) return fail(s);
+        ctx->h2d_bytes += n * 32;
         if (n && cudaMemcpyAsync(job->d_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, job->st) != cudaSuccess) {
             set_error("scalar upload failed");
             return fail(BB_ERR_CUDA);
@@ -490,6 +505,7 @@ int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint
         if (words) {
             cudaMemcpyAsync(job->d_density.p, density_bits, words * 8, cudaMemcpyHostToDevice, job->st);
             cudaMemcpyAsync(job->d_rank.p, job->h_rank.data(), words * 4, cudaMemcpyHostToDevice, job->st);
+            ctx->h2d_bytes += words * 12;
         }
         A.density = job->d_density.as<uint64_t>();
         A.density_rank = job->d_rank.as<uint32_t>();
@@ -542,6 +558,24 @@ int msm_wait_result(bb_msm_job* job, MsmResult* res) {
     }
     if (status == BB_OK) {
         bool g2 = job->group == BB_G2;
+        if (getenv("BB_DEBUG_MSM") && !g2) {
+            size_t NB = (size_t)job->W * job->D;
+            std::vector<uint32_t> off(NB + 1), srt(job->n * job->W + 1);
+            cudaMemcpy(off.data(), job->d_offsets.p, (NB + 1) * 4, cudaMemcpyDeviceToHost);
+            cudaMemcpy(srt.data(), job->d_sorted.p, job->n * job->W * 4, cudaMemcpyDeviceToHost);
+            std::vector<G1X> bk(NB);
+            cudaMemcpy(bk.data(), job->d_buckets.p, NB * sizeof(G1X), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[msm dbg] n=%zu c=%u W=%u D=%u total=%u\n", job->n, job->c, job->W, job->D, off[NB]);
+            for (size_t b = 0; b < NB; b++) {
+                if (off[b + 1] != off[b]) fprintf(stderr, "  bucket %zu: [%u,%u) first=%08x  acc.X0=%08x ZZ0=%08x\n", b, off[b], off[b + 1], srt[off[b]], bk[b].X.l[0], bk[b].ZZ.l[0]);
+                else if (!bk[b].is_identity()) fprintf(stderr, "  bucket %zu EMPTY but non-identity\n", b);
+            }
+            const G1X* win = (const G1X*)job->h_out;
+            for (uint32_t w = 0; w <= job->W; w++) if (!win[w].is_identity()) {
+                G1Affine a = win[w].to_affine();
+                fprintf(stderr, "  window %u sum affine x0=%08x%08x\n", w, a.x.l[1], a.x.l[0]);
+            }
+        }
         size_t pts = (size_t)(job->W + 1) * (g2 ? sizeof(G2X) : sizeof(G1X));
         const uint32_t* err = (const uint32_t*)((char*)job->h_out + pts);
         bool eof = err[0] != 0xffffffffu, ident = err[1] != 0;
@@ -562,6 +596,17 @@ int msm_wait_result(bb_msm_job* job, MsmResult* res) {
         }
     }
     res->status = status;
+    if (job->ev[3]) {
+        float acc_ms = 0, tot_ms = 0;
+        if (status == BB_OK && cudaEventElapsedTime(&acc_ms, job->ev[1], job->ev[2]) == cudaSuccess &&
+            cudaEventElapsedTime(&tot_ms, job->ev[0], job->ev[3]) == cudaSuccess) {
+            bool g2 = job->group == BB_G2;
+            job->ctx->prof_add(g2 ? "msm_accumulate_g2" : "msm_accumulate_g1", acc_ms, 1, job->n);
+            job->ctx->prof_add(g2 ? "msm_total_g2" : "msm_total_g1", tot_ms, 1, job->n);
+        }
+        for (auto& e : job->ev) if (e) cudaEventDestroy(e);
+        cudaGetLastError();
+    }
     if (job->h_out) cudaFreeHost(job->h_out);
     delete job;
     return status;
@@ -585,6 +630,41 @@ int bb_msm_wait(bb_msm_job* job, void* out_affine) {
     if (s != BB_OK) return s;
     if (r.g2) { G2Affine a = r.x2.to_affine(); std::memcpy(out_affine, &a, sizeof a); }
     else { G1Affine a = r.g1.to_affine(); std::memcpy(out_affine, &a, sizeof a); }
+    return BB_OK;
+}
+
+// diagnostics: out = sum_{i<D} (i+1) * P_i through k_msm_reduce + k_point_tree_sum (G1)
+int bb_selftest_bucket_reduce(bb_ctx* ctx, const void* affine_pts, uint32_t D, uint32_t K, void* out_affine) {
+    if (!ctx || !affine_pts || !out_affine || !D || !K) return BB_ERR_ARG;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    std::vector<G1X> h(D);
+    const G1Affine* a = (const G1Affine*)affine_pts;
+    for (uint32_t i = 0; i < D; i++) h[i] = G1X::from_affine(a[i]);
+    uint32_t runs = (D + K - 1) / K, nblk = (runs + 127) / 128;
+    DevBuf d_b, d_p, d_f;
+    BB_TRY(d_b.alloc(ctx, D * sizeof(G1X))); BB_TRY(d_p.alloc(ctx, nblk * sizeof(G1X))); BB_TRY(d_f.alloc(ctx, sizeof(G1X)));
+    cudaStream_t st = ctx->main_stream;
+    BB_CUDA(cudaMemcpyAsync(d_b.p, h.data(), D * sizeof(G1X), cudaMemcpyHostToDevice, st));
+    size_t sh = 128 * sizeof(G1X);
+    k_msm_reduce<Fp><<<dim3(nblk, 1), 128, sh, st>>>(d_b.as<G1X>(), D, K, d_p.as<G1X>());
+    k_point_tree_sum<Fp><<<1, 128, sh, st>>>(d_p.as<G1X>(), nblk, d_f.as<G1X>());
+    ctx->count_launch(2);
+    BB_CUDA(cudaGetLastError());
+    G1X r;
+    BB_CUDA(cudaMemcpyAsync(&r, d_f.p, sizeof r, cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    if (getenv("BB_DEBUG_MSM")) {
+        G1X p0;
+        cudaMemcpy(&p0, d_p.p, sizeof p0, cudaMemcpyDeviceToHost);
+        auto dump = [](const char* nm, const G1X& v) {
+            fprintf(stderr, "%s X=%08x.. %08x Y=%08x.. ZZ=%08x..%08x ZZZ=%08x..%08x\n", nm, v.X.l[0], v.X.l[11], v.Y.l[0], v.ZZ.l[0], v.ZZ.l[11], v.ZZZ.l[0], v.ZZZ.l[11]);
+        };
+        dump("in[0]   ", h[0]);
+        dump("partial0", p0);
+        dump("final   ", r);
+    }
+    G1Affine ra = r.to_affine();
+    std::memcpy(out_affine, &ra, sizeof ra);
     return BB_OK;
 }
 

@@ -123,8 +123,10 @@ int bb_groth16_prove_partials(bb_ctx* ctx, const bb_crs* crs, const bb_witness* 
     // witness MSMs first: they do not depend on the H pipeline (prover.rs starts them after
     // h, but all eight are in flight before the first wait, :244-318)
     cudaStream_t up = ctx->pick_stream();
-    if (w->n_inputs) BB_CUDA(cudaMemcpyAsync(d_in.p, w->input_assignment, w->n_inputs * 32, cudaMemcpyHostToDevice, up));
-    if (w->n_aux) BB_CUDA(cudaMemcpyAsync(d_aux.p, w->aux_assignment, w->n_aux * 32, cudaMemcpyHostToDevice, up));
+    const cudaMemcpyKind kind = w->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (w->n_inputs) BB_CUDA(cudaMemcpyAsync(d_in.p, w->input_assignment, w->n_inputs * 32, kind, up));
+    if (w->n_aux) BB_CUDA(cudaMemcpyAsync(d_aux.p, w->aux_assignment, w->n_aux * 32, kind, up));
+    if (!w->on_device) ctx->h2d_bytes += (w->n_inputs + w->n_aux + 3 * n) * 32;
     cudaEvent_t ev_up, ev_h;
     BB_CUDA(cudaEventCreateWithFlags(&ev_up, cudaEventDisableTiming));
     BB_CUDA(cudaEventCreateWithFlags(&ev_h, cudaEventDisableTiming));
@@ -151,7 +153,7 @@ int bb_groth16_prove_partials(bb_ctx* ctx, const bb_crs* crs, const bb_witness* 
     if (s == BB_OK) {
         auto stage = [&](DevBuf& d, const void* src) -> int {
             if (m > n) BB_CUDA(cudaMemsetAsync((char*)d.p + n * 32, 0, (m - n) * 32, st));   // coeffs.resize(m, zero), domain.rs:69
-            if (n) BB_CUDA(cudaMemcpyAsync(d.p, src, n * 32, cudaMemcpyHostToDevice, st));
+            if (n) BB_CUDA(cudaMemcpyAsync(d.p, src, n * 32, kind, st));
             return BB_OK;
         };
         if ((s = stage(d_a, w->a)) == BB_OK && (s = stage(d_b, w->b)) == BB_OK && (s = stage(d_c, w->c)) == BB_OK)

@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py -- Groth16 prover throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W             # this back-end
+    python bench.py --impl reference --gpus N --steps K ...   # restated bellman CPU path
+
+A "step" is one create_proof of the synthetic 2^20-constraint MiMC-chain R1CS (BASELINE.json
+configs[1]) from "witness vectors complete" (prover.rs:217) to "192 proof
+bytes written": 7 NTTs of 2^20, 6 G1 + 2 G2 MSMs, host finalisation.  `value` has the witness
+already resident in HBM; `e2e` goes through the public call with pinned HOST buffers, copies
+inside the timed region.  Other workloads (--workload msm | ntt) are the microbenches of
+configs[2] and configs[3].
+
+The oracle (oracle/) is used only by the cpu_baseline leg and by --impl reference.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FR_MODULUS = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+METRIC = "groth16_prove_constraints_per_sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="prove", choices=["prove", "msm", "ntt"])
+    ap.add_argument("--log-size", type=int, default=None, help="log2 of constraints (prove) / points (msm, ntt)")
+    ap.add_argument("--cpu-sample-log", type=int, default=16, help="log2 constraints of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--window-bits", type=int, default=0)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (oracle): the restated bellman rayon path, all host threads
+# ------------------------------------------------------------------------------------------------
+def cpu_prove_sample(sample_log, steps=1, warmup=0):
+    from oracle import o1
+    o1.set_threads(0)
+    cores = o1.num_threads()
+    rounds = (1 << (sample_log - 1)) - 1
+    mc = o1.Mimc(rounds, seed=7)
+    import random
+    rng = random.Random(7)
+    mc.set_toxic([rng.randrange(1, FR_MODULUS) for _ in range(5)])
+    t0 = time.perf_counter()
+    mc.generate()
+    t_gen = time.perf_counter() - t0
+    times = []
+    for i in range(warmup + steps):
+        r, s = rng.randrange(FR_MODULUS), rng.randrange(FR_MODULUS)
+        t0 = time.perf_counter()
+        mc.prove(r, s)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    n = mc.num_constraints
+    return dict(n=n, times=times, cores=cores, t_gen=t_gen,
+                sample=f"create_proof of a 2^{sample_log}-constraint MiMC chain (same circuit family as the 2^20 workload; "
+                       f"CPU cost per constraint falls ~15% from 2^{sample_log} to 2^20 as the window c = ceil(ln n) grows), "
+                       f"oracle/oracle1 C++ restatement of bellman's multicore path, {cores} threads")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_prove_sample(args.cpu_sample_log, steps=args.steps, warmup=min(args.warmup, 1))
+    total = sum(res["times"])
+    value = res["n"] * len(res["times"]) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "constraints/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / len(res["times"]),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (u64 on CPU)", "data": "synthetic",
+        "config": {"workload": "groth16-prove-2^20-mimc-chain", "sample": res["sample"]},
+        "cpu_baseline": {"value": value, "unit": "constraints/s", "cores": res["cores"], "kind": "port", "sample": res["sample"]},
+        "e2e": {"value": value, "unit": "constraints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU legs
+# ------------------------------------------------------------------------------------------------
+def random_scalars(rng, n):
+    """pseudorandom canonical scalars < 2^254 < r (dlogs of the synthetic CRS)"""
+    k = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+    k[:, 3] &= np.uint64((1 << 62) - 1)
+    return k
+
+
+def make_crs(bb, worker, shape, seed):
+    """Parameters-shaped base vectors [k_i]G with pseudorandom k_i, produced on the device.
+    Same lengths as generate_parameters' output for this circuit (generator.rs:247,303-307,
+    491-505).  Not a trapdoor CRS: valid-CRS parity at this size is
+    tests/test_gpu_parity.py::test_prove_synthetic_chain_trapdoor."""
+    rng = np.random.default_rng(seed)
+    n_a = shape["num_inputs"] + shape["a_aux_total"]
+    n_b = shape["b_in_total"] + shape["b_aux_total"]
+    mk = lambda g, n: bb.fixed_base_mul(worker, g, random_scalars(rng, n), bb.FORM_CANONICAL)
+    return dict(vk_g1=mk(bb.G1, 3), vk_g2=mk(bb.G2, 3), h=mk(bb.G1, shape["m"] - 1), l=mk(bb.G1, shape["num_aux"]),
+                a=mk(bb.G1, n_a), b_g1=mk(bb.G1, n_b), b_g2=mk(bb.G2, n_b))
+
+
+def run_prove(args):
+    import torch
+    import torch.distributed as dist
+
+    import bellman_b200 as bb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    log_n = args.log_size or 20
+    rounds = (1 << (log_n - 1)) - 1
+    worker = bb.Worker(local)
+    if args.window_bits:
+        worker.set_option("msm_window_bits", args.window_bits)
+    asg, shape = bb.synth_mimc(rounds, seed=20, pinned=True)
+    assert shape["num_constraints"] == 1 << log_n == shape["m"]
+    crs_host = make_crs(bb, worker, shape, seed=21)
+    params = bb.Parameters(worker, crs_host, shard_index=rank, shard_count=world)
+    params_full = params if world == 1 else None
+    r, s = 0x1234567 % FR_MODULUS, 0x7654321 % FR_MODULUS
+
+    # inputs resident in HBM for the `value` leg
+    dev = {}
+    keep = []
+    for name, arr in (("a", asg.a), ("b", asg.b), ("c", asg.c), ("inputs", asg.input_assignment), ("aux", asg.aux_assignment)):
+        t = torch.from_numpy(arr.view(np.int64)).to(f"cuda:{local}")
+        keep.append(t)
+        dev[name] = t.data_ptr()
+    torch.cuda.synchronize()
+    gather_buf = torch.zeros(bb.PARTIALS_BYTES, dtype=torch.uint8, device=f"cuda:{local}")
+    gathered = [torch.zeros_like(gather_buf) for _ in range(world)]
+
+    def step(device_ptrs):
+        if world == 1:
+            return bb.create_proof(asg, params, r, s, device_ptrs)
+        part = bb.prove_partials(asg, params, device_ptrs)
+        gather_buf.copy_(torch.frombuffer(bytearray(part), dtype=torch.uint8), non_blocking=False)
+        dist.all_gather(gathered, gather_buf)            # the one exchange step: per-shard partial sums
+        if rank == 0:
+            return bb.finalize(params, [bytes(g.cpu().numpy()) for g in gathered], r, s)
+        return None
+
+    def sync():
+        worker.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def timed(device_ptrs, steps, warmup):
+        proof = None
+        for _ in range(warmup):
+            proof = step(device_ptrs)
+        sync()
+        l0 = worker.kernel_launches
+        h0, d0 = worker.bytes_copied()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            proof = step(device_ptrs)
+        sync()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=f"cuda:{local}", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h1, d1 = worker.bytes_copied()
+        return dt, proof, worker.kernel_launches - l0, (h1 - h0) / steps, (d1 - d0) / steps
+
+    sampler = ClockSampler(local)
+    worker.set_option("profile", 1)
+    worker.profile_reset()
+    sampler.start()
+    dt_val, proof_val, launches, _, _ = timed(dev, args.steps, args.warmup)
+    clocks = sampler.stop()
+    acc_ms, acc_launches, acc_units = worker.profile_read("msm_accumulate_g1")
+    tot_ms, _, _ = worker.profile_read("msm_total_g1")
+    acc2_ms, acc2_launches, acc2_units = worker.profile_read("msm_accumulate_g2")
+    worker.set_option("profile", 0)
+    dt_e2e, proof_e2e, _, h2d, d2h = timed(None, args.steps, max(1, args.warmup // 2))
+    if rank == 0:
+        assert proof_val == proof_e2e and len(proof_val) == 192
+    n_constraints = shape["num_constraints"]
+    value = n_constraints * args.steps / dt_val
+    e2e = n_constraints * args.steps / dt_e2e
+    hbm_peak, peak_src = peaks()
+    # dominant kernel: G1 bucket accumulation.  Algorithmic bytes: 128 B per (base, scalar) pair
+    # (SURVEY.md 8d), pairs = scalars handed to the G1 MSMs of the timed steps (all ranks see all
+    # scalars; each accumulates its base range)
+    alg_bytes = 128.0 * acc_units / max(world, 1)
+    achieved = alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None
+    line = {
+        "metric": METRIC, "value": value, "unit": "constraints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt_val / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32 limbs (381-bit Fp / 255-bit Fr Montgomery integers)", "data": "synthetic",
+        "config": {"workload": f"groth16-prove-2^{log_n}-mimc-chain", "constraints": n_constraints, "num_aux": shape["num_aux"],
+                   "msm_sizes": {"h": shape["m"] - 1, "l": shape["num_aux"], "a": shape["a_aux_total"] + 2, "b_g1": shape["b_aux_total"] + 1,
+                                 "b_g2": shape["b_aux_total"] + 1},
+                   "ntts": "7 x 2^%d" % log_n, "parallelism": f"msm-base-range-shards x{world}, NTT replicated",
+                   "crs": "[k_i]G, pseudorandom k_i, made on device; witness: valid MiMC-chain assignment",
+                   "l2": "working set (CRS 430 MB + witness 128 MB) exceeds the 126 MB L2; no flush needed",
+                   "timing": "host wall clock over K steps bracketed by device synchronize (+barrier), max over ranks; "
+                             "kernel figures by CUDA events on the kernels' own streams"},
+        "e2e": {"value": e2e, "unit": "constraints/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * dt_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate<Fp> (G1 bucket accumulation)", "achieved": achieved, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "launches": int(acc_launches), "avg_launch_ms": acc_ms / acc_launches if acc_launches else None,
+                     "algorithmic_bytes_per_pair": 128,
+                     "share_of_step": (acc_ms / max(world, 1)) / (1e3 * dt_val) if dt_val else None,
+                     "note": "integer-ALU bound, not HBM bound (SURVEY.md 8d): see integer_roofline",
+                     "g2_accumulate_ms_per_step": acc2_ms / args.steps, "g1_msm_total_ms_per_step": tot_ms / args.steps},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        res = cpu_prove_sample(args.cpu_sample_log, steps=1, warmup=0)
+        cpu_v = res["n"] / res["times"][0]
+        line["cpu_baseline"] = {"value": cpu_v, "unit": "constraints/s", "cores": res["cores"], "kind": "port", "sample": res["sample"],
+                                "seconds": res["times"][0]}
+    else:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line))
+    worker.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_msm(args):
+    """BASELINE.json configs[2]: G1 MSM microbench (benches/slow.rs shape), 2^24 by default."""
+    import bellman_b200 as bb
+    import torch
+    log_n = args.log_size or 24
+    n = 1 << log_n
+    worker = bb.Worker(0)
+    if args.window_bits:
+        worker.set_option("msm_window_bits", args.window_bits)
+    rng = np.random.default_rng(31)
+    bases = bb.Bases(worker, bb.G1, bb.fixed_base_mul(worker, bb.G1, random_scalars(rng, n), bb.FORM_CANONICAL))
+    sc = random_scalars(rng, n)
+    d_sc = worker.device_alloc(sc.nbytes)
+    worker.upload(d_sc, sc)
+    worker.set_option("profile", 1)
+    out = None
+    for _ in range(args.warmup):
+        out = bb.multiexp_device(worker, (bases, 0), d_sc, n, bb.FORM_CANONICAL).wait()
+    worker.synchronize()
+    worker.profile_reset()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = worker.kernel_launches
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = bb.multiexp_device(worker, (bases, 0), d_sc, n, bb.FORM_CANONICAL).wait()
+    worker.synchronize()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    acc_ms, acc_l, acc_u = worker.profile_read("msm_accumulate_g1")
+    tot_ms, _, _ = worker.profile_read("msm_total_g1")
+    hbm_peak, peak_src = peaks()
+    achieved = 128.0 * n * args.steps / (tot_ms * 1e-3) / 1e9
+    line = {"metric": "g1_msm_mpt_per_sec", "value": n * args.steps / dt / 1e6, "unit": "Mpt/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32 limbs", "data": "synthetic",
+            "config": {"workload": f"g1-msm-2^{log_n}", "bases": "[k_i]G distinct", "scalars": "uniform < 2^254, canonical, resident in HBM"},
+            "gpu_launches": int(worker.kernel_launches - l0), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "whole MSM (all kernels of one job)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "accumulate_ms": acc_ms / args.steps, "device_ms": tot_ms / args.steps, "algorithmic_bytes_per_pair": 128},
+            "result_head": bytes(out[0, :2]).hex()}
+    print(json.dumps(line))
+    worker.close()
+
+
+def run_ntt(args):
+    """BASELINE.json configs[3]: Fr NTT forward + inverse, 2^24 by default, data resident in HBM."""
+    import bellman_b200 as bb
+    log_n = args.log_size or 24
+    n = 1 << log_n
+    worker = bb.Worker(0)
+    rng = np.random.default_rng(41)
+    v = random_scalars(rng, n)
+    d = worker.device_alloc(v.nbytes)
+    worker.upload(d, v)
+    for _ in range(args.warmup):
+        bb.ntt_device(worker, d, log_n, bb.NTT_FFT)
+        bb.ntt_device(worker, d, log_n, bb.NTT_IFFT)
+    worker.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = worker.kernel_launches
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        bb.ntt_device(worker, d, log_n, bb.NTT_FFT)
+        bb.ntt_device(worker, d, log_n, bb.NTT_IFFT)
+    worker.synchronize()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    back = np.zeros_like(v)
+    worker.download(d, back)
+    ok = bool(np.array_equal(back, v))                      # domain.rs:444-450 round trip, bit exact
+    hbm_peak, peak_src = peaks()
+    achieved = 2 * 64.0 * n * args.steps / dt / 1e9        # 64 B per point per transform
+    line = {"metric": "fr_ntt_mpt_per_sec", "value": 2 * n * args.steps / dt / 1e6, "unit": "Mpt/s (forward+inverse counted as 2n points)",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs", "data": "synthetic",
+            "config": {"workload": f"fr-ntt-2^{log_n}-fwd+inv", "round_trip_bit_exact": ok},
+            "gpu_launches": int(worker.kernel_launches - l0), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_ntt_pass (all passes)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_point": 64}}
+    print(json.dumps(line))
+    assert ok
+    worker.close()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.workload == "msm":
+        return run_msm(args)
+    if args.workload == "ntt":
+        return run_ntt(args)
+    return run_prove(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -163,6 +163,9 @@ typedef struct bb_witness {
     const uint64_t* a_aux_density;   /* n_aux bits   */
     const uint64_t* b_input_density; /* n_inputs bits */
     const uint64_t* b_aux_density;   /* n_aux bits   */
+    /* non-zero: a, b, c, input_assignment and aux_assignment are DEVICE pointers (inputs already
+     * resident in HBM; a, b, c are left untouched).  The density maps are always host memory. */
+    int on_device;
 } bb_witness;
 
 /* Eight partial MSM results of one proof, in the order prover.rs starts them:
@@ -179,11 +182,31 @@ int bb_groth16_finalize(const bb_crs* crs, const uint8_t* partials, size_t count
 int bb_groth16_prove(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w,
                      const uint8_t r[32], const uint8_t s[32], uint8_t proof[192]);
 
+/* ---- profiling: CUDA-event timing of the dominant kernels, on the stream they run on ------ */
+/* bb_ctx_set_option(ctx, "profile", 1) makes every MSM job bracket its bucket-accumulation
+ * kernel with cudaEvents.  bb_profile_read returns, for `what` = "msm_accumulate_g1" |
+ * "msm_accumulate_g2" | "msm_total_g1" | "msm_total_g2" | "ntt_pass", the summed device
+ * milliseconds, the number of launches (or jobs) and the number of units they processed
+ * ((base, scalar) pairs; NTT points) since the last bb_profile_reset. */
+int bb_profile_read(bb_ctx* ctx, const char* what, double* ms, uint64_t* launches, uint64_t* units);
+int bb_profile_reset(bb_ctx* ctx);
+/* bytes the MSM / prover entry points have copied host->device and device->host so far */
+int bb_ctx_bytes_copied(const bb_ctx* ctx, uint64_t* h2d, uint64_t* d2h);
+
+/* ---- synthetic workload (bench only): the MiMC chain of groth16/tests/common/mod.rs:48-129
+ *      through ProvingAssignment's bookkeeping (groth16/src/prover.rs:73-145,193-215) -------- */
+int bb_synth_mimc_shape(size_t rounds, uint64_t shape[7]);
+int bb_synth_mimc_witness(size_t rounds, uint64_t seed, uint64_t* a, uint64_t* b, uint64_t* c,
+                          uint64_t* inputs, uint64_t* aux, uint64_t* a_aux_density,
+                          uint64_t* b_input_density, uint64_t* b_aux_density);
+
 /* ---- diagnostics (used by the parity tests; not part of the bellman-facing surface) ------ */
 /* element-wise on the device: field 0 = Fr, 1 = Fp (Montgomery); op 0 mul, 1 add, 2 sub, 3 sqr */
 int bb_selftest_field(bb_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n);
 /* element-wise on affine points: op 0: a + b (mixed add); 1: 2a + b; 2: a + (2b - b) */
 int bb_selftest_point(bb_ctx* ctx, int group, int op, const void* a, const void* b, void* out, size_t n);
+/* out = sum_{i<D} (i+1) * P_i through the bucket-reduction kernels, K buckets per thread (G1) */
+int bb_selftest_bucket_reduce(bb_ctx* ctx, const void* affine_pts, uint32_t D, uint32_t K, void* out_affine);
 
 #ifdef __cplusplus
 }

@@ -22,13 +22,22 @@ __global__ void k_imad(uint32_t* out, uint32_t a, uint32_t b, int iters) {
             S(x0) S(x1) S(x2) S(x3) S(x4) S(x5) S(x6) S(x7)
 #undef S
         } else if (MODE == 2) {  // IMAD.WIDE
-#define S(x, y) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x) : "r"(y), "r"(a));
+// multiplicand = low word of the accumulator: a true dependency, nothing can be hoisted
+#define S(x, y) asm volatile("{ .reg .u32 t; cvt.u32.u64 t, %0; mad.wide.u32 %0, t, %1, %0; }" : "+l"(x) : "r"(a));
             S(w0, x0) S(w1, x1) S(w2, x2) S(w3, x3) S(w4, x4) S(w5, x5) S(w6, x6) S(w7, x7)
 #undef S
         } else if (MODE == 3) {  // IADD3 chain
 #define S(x) asm volatile("add.u32 %0, %0, %1;" : "+r"(x) : "r"(a));
             S(x0) S(x1) S(x2) S(x3) S(x4) S(x5) S(x6) S(x7)
 #undef S
+        } else if (MODE == 6) {  // mul.wide only (IMAD.WIDE.U32 with RZ addend), dependent through the low word
+#define S(x) asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo, hi}, %0; xor.b32 lo, lo, hi; mul.wide.u32 %0, lo, %1; }" : "+l"(x) : "r"(a));
+            S(w0) S(w1) S(w2) S(w3) S(w4) S(w5) S(w6) S(w7)
+#undef S
+        } else if (MODE == 5) {  // mad.lo.cc/madc.hi.cc pairs in one carry chain (IMAD.WIDE.U32.X)
+            asm volatile("mad.lo.cc.u32 %0, %0, %8, %0; madc.hi.cc.u32 %1, %0, %8, %1; madc.lo.cc.u32 %2, %2, %8, %2; madc.hi.cc.u32 %3, %2, %8, %3;"
+                         "madc.lo.cc.u32 %4, %4, %8, %4; madc.hi.cc.u32 %5, %4, %8, %5; madc.lo.cc.u32 %6, %6, %8, %6; madc.hi.u32 %7, %6, %8, %7;"
+                         : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6), "+r"(x7) : "r"(a));
         } else if (MODE == 4) {  // IMAD + IADD3 interleaved (dual pipe)
 #define S(x, y) asm volatile("mad.lo.u32 %0, %0, %2, %3; add.u32 %1, %1, %2;" : "+r"(x), "+r"(y) : "r"(a), "r"(b));
             S(x0, x4) S(x1, x5) S(x2, x6) S(x3, x7)
@@ -78,16 +87,18 @@ int main() {
     printf("device %s, %d SMs, clock %d kHz\n", prop.name, sms, prop.clockRate);
     uint32_t* d_out; CK(cudaMalloc(&d_out, 64 << 20));
     const int iters = 4096;
-    const char* names[] = {"IMAD.lo", "IMAD.hi", "IMAD.WIDE", "IADD", "IMAD+IADD"};
+    const char* names[] = {"IMAD.lo", "IMAD.hi", "IMAD.WIDE", "IADD", "IMAD+IADD", "lo/hi.cc x4", "MUL.WIDE"};
     for (int warps = 4; warps <= 32; warps *= 2) {
         int blocks = sms * 2, threads = warps * 32 / 2;
-        float ms[5];
+        float ms[7];
         ms[0] = time_kernel([&] { k_imad<0><<<blocks, threads>>>(d_out, 3, 5, iters); });
         ms[1] = time_kernel([&] { k_imad<1><<<blocks, threads>>>(d_out, 3, 5, iters); });
         ms[2] = time_kernel([&] { k_imad<2><<<blocks, threads>>>(d_out, 3, 5, iters); });
         ms[3] = time_kernel([&] { k_imad<3><<<blocks, threads>>>(d_out, 3, 5, iters); });
         ms[4] = time_kernel([&] { k_imad<4><<<blocks, threads>>>(d_out, 3, 5, iters); });
-        for (int m = 0; m < 5; m++) {
+        ms[5] = time_kernel([&] { k_imad<5><<<blocks, threads>>>(d_out, 3, 5, iters); });
+        ms[6] = time_kernel([&] { k_imad<6><<<blocks, threads>>>(d_out, 3, 5, iters); });
+        for (int m = 0; m < 7; m++) {
             double ops = (double)blocks * threads * iters * 8;   // per-thread instructions of the named kind (mode 4: 4 IMAD + 4 IADD)
             printf("warps/SM %2d  %-10s %8.3f ms  %7.1f Gop/s  %6.1f op/clk/SM @1.9GHz\n", warps, names[m], ms[m], ops / ms[m] / 1e6,
                    ops / (ms[m] * 1e-3) / sms / 1.9e9);
