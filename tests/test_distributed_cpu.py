@@ -1,0 +1,57 @@
+"""N>1 host logic on CPU (gloo, world_size 2): shard ranges, the all-gather of partial-sum
+blobs, and the host-side addition of per-shard partials (bb_point_add runs on the host).  The
+per-shard sums themselves come from the CPU oracle here; on the GPU box the same plumbing carries
+the device results (bench.py --gpus N, tests/test_gpu_parity.py's sharded finalize)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent('''
+    import os, sys
+    import numpy as np
+    import torch.distributed as dist
+    sys.path.insert(0, os.environ["BB_ROOT"])
+    import bellman_b200 as bb
+    from bellman_b200.distributed import shard_range, all_gather_partials, max_over_ranks
+    from oracle import o1
+
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n = 301
+    bases = o1.g1_fixed_mul(o1.fr_random(1, n))
+    ex = o1.fr_random(2, n)
+    lo, hi = shard_range(n, rank, world)
+    rc, part = o1.multiexp(1, bases[lo:hi], 0, None, ex[lo:hi])      # this rank's base range
+    assert rc == 0
+    blob = bytearray(bb.PARTIALS_BYTES)
+    blob[0:96] = part.tobytes()                                       # slot 0 = the "h" partial
+    blob[96] = rank                                                   # marker to check ordering
+    got = all_gather_partials(bytes(blob))
+    assert [g[96] for g in got] == list(range(world))
+    total = np.zeros((1, 12), np.uint64)
+    for g in got:
+        total = bb.point_add(bb.G1, total, np.frombuffer(g[:96], dtype=np.uint64).reshape(1, 12))
+    rc, want = o1.multiexp(1, bases, 0, None, ex)
+    assert rc == 0 and np.array_equal(total, want)
+    assert max_over_ranks(float(rank)) == world - 1
+    ranges = [shard_range(n, r, world) for r in range(world)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == n and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    dist.destroy_process_group()
+    print("rank", rank, "ok")
+''')
+
+
+def test_sharded_partials_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, BB_ROOT=ROOT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", str(script)]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "rank 0 ok" in res.stdout and "rank 1 ok" in res.stdout
