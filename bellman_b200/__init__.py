@@ -175,6 +175,17 @@ class Bases:
                                               C.c_size_t(global_offset), C.c_size_t(global_len), C.byref(h)))
         self._h = h
 
+    @classmethod
+    def synthetic(cls, worker, group, seed, n, global_offset=0, global_len=None):
+        """bench-only: [k_i]G with counter-based pseudorandom k_i, generated in HBM (no host copy)."""
+        self = cls.__new__(cls)
+        self.worker, self.group, self.n = worker, group, n
+        h = C.c_void_p()
+        _check(load_library().bb_synth_bases(worker._h, C.c_int(group), C.c_uint64(seed), C.c_size_t(n), C.c_size_t(global_offset),
+                                             C.c_size_t(n if global_len is None else global_len), C.byref(h)))
+        self._h = h
+        return self
+
     def free(self):
         if getattr(self, "_h", None):
             load_library().bb_bases_free(self._h)
@@ -374,6 +385,20 @@ class Parameters:
         _check(load_library().bb_crs_create(worker._h, C.byref(d), C.byref(h)))
         self._h = h
 
+    @classmethod
+    def synthetic(cls, worker, seed, shape, shard_index=0, shard_count=1):
+        """bench-only: Parameters-shaped vectors [k_i]G generated on the device for this rank's
+        base-range shard (lengths as generate_parameters would produce for `shape`)."""
+        self = cls.__new__(cls)
+        self.worker, self._keep = worker, None
+        h = C.c_void_p()
+        _check(load_library().bb_synth_crs(worker._h, C.c_uint64(seed), C.c_size_t(shape["m"] - 1), C.c_size_t(shape["num_aux"]),
+                                           C.c_size_t(shape["num_inputs"] + shape["a_aux_total"]),
+                                           C.c_size_t(shape["b_in_total"] + shape["b_aux_total"]),
+                                           C.c_uint32(shard_index), C.c_uint32(shard_count), C.byref(h)))
+        self._h = h
+        return self
+
     def free(self):
         if getattr(self, "_h", None):
             load_library().bb_crs_destroy(self._h)
@@ -482,3 +507,8 @@ def synth_mimc(rounds, seed, pinned=False):
     asg._keep = keep
     return asg, dict(num_inputs=ni, num_aux=na, num_constraints=n, m=int(shape[3]), a_aux_total=int(shape[4]),
                      b_in_total=int(shape[5]), b_aux_total=int(shape[6]))
+
+
+def synth_scalars_device(worker, seed, n, d_ptr):
+    """bench-only: fill a device buffer with n pseudorandom canonical scalars (< 2^254)."""
+    _check(load_library().bb_synth_scalars_device(worker._h, C.c_uint64(seed), C.c_size_t(n), d_ptr))

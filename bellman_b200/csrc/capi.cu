@@ -122,6 +122,21 @@ __global__ void __launch_bounds__(128) k_fixed_base_mul(const Affine<F>* __restr
 }
 
 template <class F>
+int fixed_base_mul_dev(bb_ctx* ctx, FixedTable<F>& tab, const Affine<F>& gen, const Fr* d_scalars, size_t n, bool montgomery,
+                       Affine<F>* d_out, cudaStream_t st) {
+    {
+        std::lock_guard<std::mutex> g(g_tab_mu);
+        BB_TRY(build_fixed_table(tab, gen));
+    }
+    if (n) {
+        k_fixed_base_mul<F><<<cdiv(n, 128), 128, 0, st>>>(tab.d_table, d_scalars, n, montgomery, d_out);
+        ctx->count_launch();
+    }
+    BB_CUDA(cudaGetLastError());
+    return BB_OK;
+}
+
+template <class F>
 int fixed_base_mul(bb_ctx* ctx, FixedTable<F>& tab, const Affine<F>& gen, const void* scalars, size_t n, int form, void* out) {
     {
         std::lock_guard<std::mutex> g(g_tab_mu);
@@ -176,6 +191,13 @@ int selftest_run(bb_ctx* ctx, K kernel, const void* a, const void* b, void* o, s
 }
 
 }  // namespace
+
+namespace bb {
+int fixed_base_mul_device(bb_ctx* ctx, int group, const Fr* d_scalars, size_t n, bool montgomery, void* d_out, cudaStream_t st) {
+    if (group == BB_G1) return fixed_base_mul_dev<Fp>(ctx, g_tab1, g1_generator(), d_scalars, n, montgomery, (G1Affine*)d_out, st);
+    return fixed_base_mul_dev<Fp2>(ctx, g_tab2, g2_generator(), d_scalars, n, montgomery, (G2Affine*)d_out, st);
+}
+}  // namespace bb
 
 extern "C" {
 

@@ -73,6 +73,9 @@ G2X g2_host_mul(const G2X& p, const uint32_t* k) { return host_mul<Fp2>(p, k); }
 
 extern "C" {
 
+int bb_synth_bases(bb_ctx* ctx, int group, uint64_t seed, size_t n, size_t global_offset, size_t global_len, bb_bases** out);
+void bb_crs_destroy(bb_crs* crs);
+
 int bb_crs_create(bb_ctx* ctx, const bb_crs_desc* d, bb_crs** out) {
     if (!ctx || !d || !out) { set_error("bb_crs_create: null argument"); return BB_ERR_ARG; }
     if (!d->alpha_g1 || !d->beta_g1 || !d->delta_g1 || !d->beta_g2 || !d->delta_g2) { set_error("bb_crs_create: missing vk element"); return BB_ERR_ARG; }
@@ -95,6 +98,36 @@ int bb_crs_create(bb_ctx* ctx, const bb_crs_desc* d, bb_crs** out) {
         bb_crs_destroy(crs);
         return s;
     }
+    *out = crs;
+    return BB_OK;
+}
+
+// Synthetic Parameters for the benchmark: every vector is [k_i]G with counter-based pseudorandom
+// k_i, generated on the device directly into this rank's base-range shard.  Same vector lengths a
+// real key has; not a trapdoor CRS (parity with a valid CRS at this size lives in tests/).
+int bb_synth_crs(bb_ctx* ctx, uint64_t seed, size_t h_len, size_t l_len, size_t a_len, size_t b_len,
+                 uint32_t shard_index, uint32_t shard_count, bb_crs** out) {
+    if (!ctx || !out || !shard_count || shard_index >= shard_count) return BB_ERR_ARG;
+    bb_crs* crs = new bb_crs();
+    crs->ctx = ctx; crs->shard_index = shard_index; crs->shard_count = shard_count;
+    uint64_t k1[3][4], k2[2][4];
+    for (int i = 0; i < 3; i++) { k1[i][0] = seed * 7 + i + 11; k1[i][1] = seed + 3 * i; k1[i][2] = 5 + i; k1[i][3] = 1 + i; }
+    for (int i = 0; i < 2; i++) { k2[i][0] = seed * 13 + i + 17; k2[i][1] = seed + 5 * i; k2[i][2] = 9 + i; k2[i][3] = 2 + i; }
+    G1Affine v1[3]; G2Affine v2[2];
+    int s = bb_fixed_base_mul(ctx, BB_G1, k1, 3, BB_FORM_CANONICAL, v1);
+    if (s == BB_OK) s = bb_fixed_base_mul(ctx, BB_G2, k2, 2, BB_FORM_CANONICAL, v2);
+    crs->alpha_g1 = v1[0]; crs->beta_g1 = v1[1]; crs->delta_g1 = v1[2];
+    crs->beta_g2 = v2[0]; crs->delta_g2 = v2[1];
+    auto gen = [&](int group, uint64_t sd, size_t len, bb_bases** dst) -> int {
+        size_t lo = len * shard_index / shard_count, hi = len * (shard_index + 1) / shard_count;
+        return bb_synth_bases(ctx, group, sd, hi - lo, lo, len, dst);
+    };
+    if (s == BB_OK) s = gen(BB_G1, seed + 1, h_len, &crs->h);
+    if (s == BB_OK) s = gen(BB_G1, seed + 2, l_len, &crs->l);
+    if (s == BB_OK) s = gen(BB_G1, seed + 3, a_len, &crs->a);
+    if (s == BB_OK) s = gen(BB_G1, seed + 4, b_len, &crs->b_g1);
+    if (s == BB_OK) s = gen(BB_G2, seed + 4, b_len, &crs->b_g2);       // same dlogs in G1 and G2, like a real B query
+    if (s != BB_OK) { bb_crs_destroy(crs); return s; }
     *out = crs;
     return BB_OK;
 }

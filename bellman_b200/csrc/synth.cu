@@ -39,9 +39,59 @@ Fr random_fr(SplitMix& g) {
 inline void put(uint64_t* dst, size_t i, const Fr& v) { std::memcpy(dst + 4 * i, v.l, 32); }
 inline void set_bit(uint64_t* bits, size_t i) { bits[i >> 6] |= 1ull << (i & 63); }
 
+// canonical scalars < 2^254 < r from a counter-based generator: element i of stream `seed` is the
+// same on every device, so base-range shards of a synthetic CRS agree across ranks
+__global__ void __launch_bounds__(256) k_synth_scalars(Fr* out, size_t n, uint64_t seed, uint64_t first) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr v;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint64_t z = seed + 0x9E3779B97F4A7C15ull * (4 * (first + i) + j + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        if (j == 3) z &= 0x3fffffffffffffffull;
+        v.l[2 * j] = (uint32_t)z;
+        v.l[2 * j + 1] = (uint32_t)(z >> 32);
+    }
+    out[i] = v;
+}
+
 }  // namespace
 
 extern "C" {
+
+// d_out[i] = pseudorandom canonical scalar < 2^254, i < n, resident in HBM (bench inputs)
+int bb_synth_scalars_device(bb_ctx* ctx, uint64_t seed, size_t n, void* d_out) {
+    if (!ctx || (n && !d_out)) return BB_ERR_ARG;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    if (n) { k_synth_scalars<<<cdiv(n, 256), 256, 0, ctx->main_stream>>>((Fr*)d_out, n, seed, 0); ctx->count_launch(); }
+    BB_CUDA(cudaGetLastError());
+    BB_CUDA(cudaStreamSynchronize(ctx->main_stream));
+    return BB_OK;
+}
+
+// Base vector [k_i]G, k_i = stream `seed`, produced on the device straight into a bb_bases
+// (no host round trip): global indices [global_offset, global_offset + n) of a vector of global_len.
+int bb_synth_bases(bb_ctx* ctx, int group, uint64_t seed, size_t n, size_t global_offset, size_t global_len, bb_bases** out) {
+    if (!ctx || !out || (group != BB_G1 && group != BB_G2) || global_offset + n > global_len) return BB_ERR_ARG;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    size_t stride = group == BB_G1 ? sizeof(G1Affine) : sizeof(G2Affine);
+    void* d = nullptr;
+    BB_TRY(ctx->alloc((n ? n : 1) * stride, &d));
+    DevBuf d_k;
+    BB_TRY(d_k.alloc(ctx, n * 32));
+    cudaStream_t st = ctx->main_stream;
+    if (n) { k_synth_scalars<<<cdiv(n, 256), 256, 0, st>>>(d_k.as<Fr>(), n, seed, global_offset); ctx->count_launch(); }
+    int s = fixed_base_mul_device(ctx, group, d_k.as<Fr>(), n, false, d, st);
+    if (s == BB_OK && cudaStreamSynchronize(st) != cudaSuccess) s = BB_ERR_CUDA;
+    if (s != BB_OK) { ctx->release(d); return s; }
+    bb_bases* b = new bb_bases();
+    b->ctx = ctx; b->group = group; b->d_points = d; b->n = n; b->global_offset = global_offset; b->global_len = global_len;
+    *out = b;
+    return BB_OK;
+}
 
 // shape[0..6] = num_inputs, num_aux, num_constraints, m, a_aux_density_total,
 //               b_input_density_total, b_aux_density_total

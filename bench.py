@@ -45,6 +45,13 @@ def parse():
     return ap.parse_args()
 
 
+T0 = time.time()
+
+
+def log(msg):
+    print(f"[bench +{time.time() - T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -194,11 +201,12 @@ def run_prove(args):
     worker = bb.Worker(local)
     if args.window_bits:
         worker.set_option("msm_window_bits", args.window_bits)
+    log("synthesising the MiMC-chain witness (CPU, product-side generator)")
     asg, shape = bb.synth_mimc(rounds, seed=20, pinned=True)
     assert shape["num_constraints"] == 1 << log_n == shape["m"]
-    crs_host = make_crs(bb, worker, shape, seed=21)
-    params = bb.Parameters(worker, crs_host, shard_index=rank, shard_count=world)
-    params_full = params if world == 1 else None
+    log("generating the synthetic CRS on the device")
+    params = bb.Parameters.synthetic(worker, 21, shape, shard_index=rank, shard_count=world)
+    log("CRS resident")
     r, s = 0x1234567 % FR_MODULUS, 0x7654321 % FR_MODULUS
 
     # inputs resident in HBM for the `value` leg
@@ -247,6 +255,7 @@ def run_prove(args):
         h1, d1 = worker.bytes_copied()
         return dt, proof, worker.kernel_launches - l0, (h1 - h0) / steps, (d1 - d0) / steps
 
+    log("timed region: inputs resident in HBM")
     sampler = ClockSampler(local)
     worker.set_option("profile", 1)
     worker.profile_reset()
@@ -257,7 +266,9 @@ def run_prove(args):
     tot_ms, _, _ = worker.profile_read("msm_total_g1")
     acc2_ms, acc2_launches, acc2_units = worker.profile_read("msm_accumulate_g2")
     worker.set_option("profile", 0)
+    log(f"value leg done: {1e3 * dt_val / args.steps:.2f} ms/step; timed region: host buffers (e2e)")
     dt_e2e, proof_e2e, _, h2d, d2h = timed(None, args.steps, max(1, args.warmup // 2))
+    log(f"e2e leg done: {1e3 * dt_e2e / args.steps:.2f} ms/step")
     if rank == 0:
         assert proof_val == proof_e2e and len(proof_val) == 192
     n_constraints = shape["num_constraints"]
@@ -294,7 +305,9 @@ def run_prove(args):
                      "g2_accumulate_ms_per_step": acc2_ms / args.steps, "g1_msm_total_ms_per_step": tot_ms / args.steps},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        log("cpu_baseline leg (oracle, all host threads)")
         res = cpu_prove_sample(args.cpu_sample_log, steps=1, warmup=0)
+        log("cpu_baseline done")
         cpu_v = res["n"] / res["times"][0]
         line["cpu_baseline"] = {"value": cpu_v, "unit": "constraints/s", "cores": res["cores"], "kind": "port", "sample": res["sample"],
                                 "seconds": res["times"][0]}
@@ -316,11 +329,11 @@ def run_msm(args):
     worker = bb.Worker(0)
     if args.window_bits:
         worker.set_option("msm_window_bits", args.window_bits)
-    rng = np.random.default_rng(31)
-    bases = bb.Bases(worker, bb.G1, bb.fixed_base_mul(worker, bb.G1, random_scalars(rng, n), bb.FORM_CANONICAL))
-    sc = random_scalars(rng, n)
-    d_sc = worker.device_alloc(sc.nbytes)
-    worker.upload(d_sc, sc)
+    log("generating bases and scalars on the device")
+    bases = bb.Bases.synthetic(worker, bb.G1, 31, n)
+    d_sc = worker.device_alloc(n * 32)
+    bb.synth_scalars_device(worker, 32, n, d_sc)
+    log("inputs resident")
     worker.set_option("profile", 1)
     out = None
     for _ in range(args.warmup):
@@ -343,7 +356,8 @@ def run_msm(args):
     line = {"metric": "g1_msm_mpt_per_sec", "value": n * args.steps / dt / 1e6, "unit": "Mpt/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32 limbs", "data": "synthetic",
-            "config": {"workload": f"g1-msm-2^{log_n}", "bases": "[k_i]G distinct", "scalars": "uniform < 2^254, canonical, resident in HBM"},
+            "config": {"workload": f"g1-msm-2^{log_n}", "bases": "[k_i]G distinct, generated in HBM", "scalars": "pseudorandom < 2^254, canonical, resident in HBM",
+                       "window_bits": args.window_bits or "auto"},
             "gpu_launches": int(worker.kernel_launches - l0), "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "whole MSM (all kernels of one job)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
@@ -359,10 +373,10 @@ def run_ntt(args):
     log_n = args.log_size or 24
     n = 1 << log_n
     worker = bb.Worker(0)
-    rng = np.random.default_rng(41)
-    v = random_scalars(rng, n)
-    d = worker.device_alloc(v.nbytes)
-    worker.upload(d, v)
+    d = worker.device_alloc(n * 32)
+    bb.synth_scalars_device(worker, 41, n, d)
+    v = np.zeros((n, 4), np.uint64)
+    worker.download(d, v)
     for _ in range(args.warmup):
         bb.ntt_device(worker, d, log_n, bb.NTT_FFT)
         bb.ntt_device(worker, d, log_n, bb.NTT_IFFT)

@@ -195,6 +195,13 @@ int bb_ctx_bytes_copied(const bb_ctx* ctx, uint64_t* h2d, uint64_t* d2h);
 
 /* ---- synthetic workload (bench only): the MiMC chain of groth16/tests/common/mod.rs:48-129
  *      through ProvingAssignment's bookkeeping (groth16/src/prover.rs:73-145,193-215) -------- */
+/* pseudorandom canonical scalars (< 2^254) generated in HBM */
+int bb_synth_scalars_device(bb_ctx* ctx, uint64_t seed, size_t n, void* d_out);
+/* base vector [k_i]G with counter-based pseudorandom k_i, made on the device straight into a
+ * bb_bases / bb_crs (shard-consistent across ranks) */
+int bb_synth_bases(bb_ctx* ctx, int group, uint64_t seed, size_t n, size_t global_offset, size_t global_len, bb_bases** out);
+int bb_synth_crs(bb_ctx* ctx, uint64_t seed, size_t h_len, size_t l_len, size_t a_len, size_t b_len,
+                 uint32_t shard_index, uint32_t shard_count, bb_crs** out);
 int bb_synth_mimc_shape(size_t rounds, uint64_t shape[7]);
 int bb_synth_mimc_witness(size_t rounds, uint64_t seed, uint64_t* a, uint64_t* b, uint64_t* c,
                           uint64_t* inputs, uint64_t* aux, uint64_t* a_aux_density,
