@@ -14,6 +14,7 @@ but creating a Worker without the built library or without a CUDA device raises.
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -109,9 +110,12 @@ class Worker:
         _check(lib.bb_ctx_create(C.c_int(device), C.byref(h)))
         self._h = h
         self.device = device
+        self._children = weakref.WeakSet()      # Bases / Parameters living on this context
 
     def close(self):
         if getattr(self, "_h", None):
+            for child in list(self._children):  # device objects must go before their context
+                child.free()
             load_library().bb_ctx_destroy(self._h)
             self._h = None
 
@@ -174,6 +178,7 @@ class Bases:
         _check(load_library().bb_bases_upload(worker._h, C.c_int(group), _ptr(pts), C.c_size_t(pts.shape[0]),
                                               C.c_size_t(global_offset), C.c_size_t(global_len), C.byref(h)))
         self._h = h
+        worker._children.add(self)
 
     @classmethod
     def synthetic(cls, worker, group, seed, n, global_offset=0, global_len=None):
@@ -184,6 +189,7 @@ class Bases:
         _check(load_library().bb_synth_bases(worker._h, C.c_int(group), C.c_uint64(seed), C.c_size_t(n), C.c_size_t(global_offset),
                                              C.c_size_t(n if global_len is None else global_len), C.byref(h)))
         self._h = h
+        worker._children.add(self)
         return self
 
     def free(self):
@@ -384,6 +390,7 @@ class Parameters:
         h = C.c_void_p()
         _check(load_library().bb_crs_create(worker._h, C.byref(d), C.byref(h)))
         self._h = h
+        worker._children.add(self)
 
     @classmethod
     def synthetic(cls, worker, seed, shape, shard_index=0, shard_count=1):
@@ -397,6 +404,7 @@ class Parameters:
                                            C.c_size_t(shape["b_in_total"] + shape["b_aux_total"]),
                                            C.c_uint32(shard_index), C.c_uint32(shard_count), C.byref(h)))
         self._h = h
+        worker._children.add(self)
         return self
 
     def free(self):

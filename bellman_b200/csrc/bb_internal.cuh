@@ -53,6 +53,7 @@ struct bb_ctx {
     long opt_ntt_tile_log = 11;
     long opt_ntt_col_bits = 3;
     long opt_profile = 0;
+    long opt_msm_acc_variant = 0;
     struct ProfEntry { double ms = 0; uint64_t launches = 0, units = 0; };
     std::map<std::string, ProfEntry> prof;
     void prof_add(const char* what, double ms, uint64_t launches, uint64_t units) {
@@ -62,6 +63,12 @@ struct bb_ctx {
     }
     std::map<uint32_t, bb::NttTables*> ntt_tables;   // by log_n
 
+    // small page-locked staging blocks for results (cudaMallocHost/cudaFreeHost synchronise the
+    // device and are slow; jobs borrow fixed-size blocks instead)
+    static constexpr size_t PINNED_BLOCK = 64 * 1024;
+    std::vector<void*> pinned_free;
+    int pinned_acquire(size_t bytes, void** out);
+    void pinned_release(void* p);
     int alloc(size_t bytes, void** out);
     void release(void* p);
     cudaStream_t pick_stream();

@@ -55,6 +55,19 @@ void bb_ctx::release(void* p) {
     free_blocks.emplace(it->second, p);
     live_blocks.erase(it);
 }
+int bb_ctx::pinned_acquire(size_t bytes, void** out) {
+    if (bytes > PINNED_BLOCK) { set_error("pinned staging block too small for %zu bytes", bytes); return BB_ERR_ARG; }
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (!pinned_free.empty()) { *out = pinned_free.back(); pinned_free.pop_back(); return BB_OK; }
+    }
+    BB_CUDA(cudaMallocHost(out, PINNED_BLOCK));
+    return BB_OK;
+}
+void bb_ctx::pinned_release(void* p) {
+    std::lock_guard<std::mutex> g(mu);
+    pinned_free.push_back(p);
+}
 cudaStream_t bb_ctx::pick_stream() {
     std::lock_guard<std::mutex> g(mu);
     cudaStream_t s = streams[next_stream % streams.size()];
@@ -236,6 +249,7 @@ void bb_ctx_destroy(bb_ctx* ctx) {
     cudaDeviceSynchronize();
     for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
     for (auto& kv : ctx->live_blocks) cudaFree(kv.first);
+    for (auto p : ctx->pinned_free) cudaFreeHost(p);
     for (auto s : ctx->streams) cudaStreamDestroy(s);
     if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
     // NTT tables are freed with the process; they are keyed by size and shared
@@ -249,6 +263,7 @@ int bb_ctx_set_option(bb_ctx* ctx, const char* key, long value) {
     else if (k == "ntt_tile_log") ctx->opt_ntt_tile_log = value;
     else if (k == "ntt_col_bits") ctx->opt_ntt_col_bits = value;
     else if (k == "profile") ctx->opt_profile = value;
+    else if (k == "msm_acc_variant") ctx->opt_msm_acc_variant = value;
     else { set_error("unknown option %s", key); return BB_ERR_ARG; }
     return BB_OK;
 }

@@ -23,6 +23,7 @@
 // Error semantics (Source::next / skip, :53-86) are reproduced, see bb_msm_wait.
 #include <cmath>
 #include <cstdlib>
+#include <ctime>
 
 #include "bb_internal.cuh"
 
@@ -204,13 +205,46 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_finish(uint32_t* out, uin
     }
 }
 
-// ---- bucket accumulation ------------------------------------------------------------------
-template <class F>
-__global__ void __launch_bounds__(128) k_msm_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ offsets,
-                                                        const uint32_t* __restrict__ sorted, XYZZ<F>* buckets, size_t nb,
-                                                        uint32_t* err) {
+// ---- bucket order: heaviest first, equal sizes adjacent --------------------------------------
+// One thread owns one bucket, so a warp runs as long as its largest bucket: with Poisson-sized
+// buckets only ~72% of the lanes do useful work (measured).  Handing the threads buckets in
+// order of size (a counting sort over the sizes, three tiny kernels) makes the 32 buckets of a
+// warp equally long and schedules the long ones first.
+constexpr uint32_t SIZE_BINS = 4096;      // sizes >= SIZE_BINS-1 share the last bin
+
+__global__ void __launch_bounds__(256) k_size_hist(const uint32_t* __restrict__ offsets, size_t nb, uint32_t* size_hist) {
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
+    uint32_t sz = offsets[b + 1] - offsets[b];
+    atomicAdd(&size_hist[sz < SIZE_BINS - 1 ? sz : SIZE_BINS - 1], 1u);
+}
+// size_hist[s] <- first position of size class s in the descending order
+__global__ void __launch_bounds__(1024) k_size_scan(uint32_t* size_hist) {
+    __shared__ uint32_t sh[SIZE_BINS];
+    for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) sh[i] = size_hist[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int s = SIZE_BINS - 1; s >= 0; s--) { uint32_t c = sh[s]; sh[s] = run; run += c; }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) size_hist[i] = sh[i];
+}
+__global__ void __launch_bounds__(256) k_size_order(const uint32_t* __restrict__ offsets, size_t nb, uint32_t* size_cursor, uint32_t* order) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    uint32_t sz = offsets[b + 1] - offsets[b];
+    order[atomicAdd(&size_cursor[sz < SIZE_BINS - 1 ? sz : SIZE_BINS - 1], 1u)] = (uint32_t)b;
+}
+
+// ---- bucket accumulation ------------------------------------------------------------------
+template <class F, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ offsets,
+                                                        const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ order,
+                                                        XYZZ<F>* buckets, size_t nb, uint32_t* err) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb) return;
+    const uint32_t b = order[t];
     uint32_t start = offsets[b], end = offsets[b + 1];
     XYZZ<F> acc = XYZZ<F>::identity();
     for (uint32_t k = start; k < end; k++) {
@@ -343,7 +377,7 @@ struct bb_msm_job {
     size_t n = 0;
     int status = BB_OK;              // pre-launch failure, reported at wait()
     DigitArgs dargs{};
-    DevBuf d_scalars, d_density, d_rank, d_counts, d_offsets, d_tiles, d_sorted, d_buckets, d_partials, d_final, d_ones, d_err;
+    DevBuf d_scalars, d_density, d_rank, d_counts, d_offsets, d_tiles, d_sorted, d_order, d_buckets, d_partials, d_final, d_ones, d_err;
     std::vector<uint32_t> h_rank;
     void* h_out = nullptr;           // pinned: [W window sums][1 ones sum] then err[4]
     size_t h_out_bytes = 0;
@@ -354,17 +388,28 @@ namespace {
 
 uint32_t choose_window(bb_ctx* ctx, size_t n) {
     if (ctx->opt_msm_window_bits >= 2 && ctx->opt_msm_window_bits <= 24) return (uint32_t)ctx->opt_msm_window_bits;
+    // Signed-digit windows of c bits: W = floor(255/c)+1 windows, the top one holding only
+    // tb = 255 - (W-1)c scalar bits.  A top window with few bits has few live buckets, i.e.
+    // little parallelism for a thread-per-bucket accumulation (c = 14: 3 bits -> a handful of
+    // threads own n/8 additions each).  Only window sizes whose top window is (nearly) full
+    // are used: 4 (tb 3), 8 (tb 7), 16 (tb 15), 20 (tb 15).
     if (n < 32) return 4;
-    // minimise  W * (n + 3 * 2^(c-1))  with W = 255/c + 1: accumulation adds + reduction adds
-    uint32_t best = 4;
-    double best_cost = 1e300;
-    for (uint32_t c = 4; c <= 22; c++) {
-        double W = 255 / c + 1;
-        double cost = W * ((double)n + 3.0 * (double)(1u << (c - 1)));
-        if (cost < best_cost) { best_cost = cost; best = c; }
-    }
-    return best;
+    if (n < (1u << 13)) return 8;
+    if (n < (1u << 23)) return 16;
+    return 20;
 }
+
+// BB_TRACE=1: synchronise after every stage and report it (debugging aid, off the hot path)
+static bool trace_on() { static int v = -1; if (v < 0) v = getenv("BB_TRACE") ? 1 : 0; return v == 1; }
+#define BB_STAGE(name)                                                                            \
+    do {                                                                                          \
+        if (trace_on()) {                                                                         \
+            cudaError_t e_ = cudaStreamSynchronize(st);                                           \
+            struct timespec ts_; clock_gettime(CLOCK_MONOTONIC, &ts_);                            \
+            fprintf(stderr, "[bb trace %8.3f] msm n=%zu c=%u W=%u %-12s %s\n", ts_.tv_sec % 1000 + ts_.tv_nsec * 1e-9, job->n, job->c, job->W, name, cudaGetErrorString(e_)); \
+            fflush(stderr);                                                                       \
+        }                                                                                         \
+    } while (0)
 
 template <class F>
 int launch_msm(bb_msm_job* job) {
@@ -381,6 +426,7 @@ int launch_msm(bb_msm_job* job) {
     BB_TRY(job->d_ones.alloc(ctx, (n + 4) * 4));
     BB_TRY(job->d_err.alloc(ctx, 16));
     BB_TRY(job->d_buckets.alloc(ctx, NB * sizeof(XYZZ<F>)));
+    BB_TRY(job->d_order.alloc(ctx, (NB + SIZE_BINS) * 4));
     // reduction geometry: K buckets per thread, 128 threads per CTA
     uint32_t K = 16;
     while (K > 1 && (D / K) < 128) K >>= 1;
@@ -406,28 +452,43 @@ int launch_msm(bb_msm_job* job) {
     A.ones_count = job->d_ones.as<uint32_t>();
     A.ones_list = job->d_ones.as<uint32_t>() + 4;
     A.err = job->d_err.as<uint32_t>();
+    BB_STAGE("setup");
     if (n) {
         A.mode = 0;
         k_msm_digits<<<cdiv(n, 256), 256, 0, st>>>(A);
         ctx->count_launch();
     }
+    BB_STAGE("histogram");
     uint32_t* offsets = job->d_offsets.as<uint32_t>();
     k_scan_tiles<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(A.counts, offsets, NB, job->d_tiles.as<uint32_t>());
     k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(job->d_tiles.as<uint32_t>(), ntiles);
     // cursors live in the histogram buffer: after this kernel counts[] holds bucket starts
     k_scan_finish<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(offsets, A.counts, NB, job->d_tiles.as<uint32_t>(), A.counts);
     ctx->count_launch(3);
+    BB_STAGE("scan");
     if (n) {
         A.mode = 1;
         k_msm_digits<<<cdiv(n, 256), 256, 0, st>>>(A);
         ctx->count_launch();
     }
+    BB_STAGE("scatter");
     const Affine<F>* bases = (const Affine<F>*)job->bases->d_points;
     XYZZ<F>* buckets = job->d_buckets.as<XYZZ<F>>();
+    uint32_t* order = job->d_order.as<uint32_t>();
+    uint32_t* size_hist = order + NB;
+    BB_CUDA(cudaMemsetAsync(size_hist, 0, SIZE_BINS * 4, st));
+    k_size_hist<<<cdiv(NB, 256), 256, 0, st>>>(offsets, NB, size_hist);
+    k_size_scan<<<1, 1024, 0, st>>>(size_hist);
+    k_size_order<<<cdiv(NB, 256), 256, 0, st>>>(offsets, NB, size_hist, order);
+    ctx->count_launch(3);
+    BB_STAGE("order");
     if (prof) BB_CUDA(cudaEventRecord(job->ev[1], st));
-    k_msm_accumulate<F><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, buckets, NB, A.err);
+    if (ctx->opt_msm_acc_variant == 1) k_msm_accumulate<F, 4><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, A.err);
+    else if (ctx->opt_msm_acc_variant == 2) k_msm_accumulate<F, 5><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, A.err);
+    else k_msm_accumulate<F, 1><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, A.err);
     ctx->count_launch();
     if (prof) BB_CUDA(cudaEventRecord(job->ev[2], st));
+    BB_STAGE("accumulate");
     XYZZ<F>* partials = job->d_partials.as<XYZZ<F>>();
     size_t sh = 128 * sizeof(XYZZ<F>);
     if (sh > 48 * 1024) {
@@ -441,10 +502,11 @@ int launch_msm(bb_msm_job* job) {
     k_point_tree_sum<F><<<W, 128, sh, st>>>(partials, nblk, fin);
     k_point_tree_sum<F><<<1, 128, sh, st>>>(partials + (size_t)W * nblk, ONES_BLOCKS, fin + W);
     ctx->count_launch(4);
+    BB_STAGE("reduce");
     BB_CUDA(cudaGetLastError());
     size_t pts = (size_t)(W + 1) * sizeof(XYZZ<F>);
     job->h_out_bytes = pts + 16;
-    BB_CUDA(cudaMallocHost(&job->h_out, job->h_out_bytes));
+    BB_TRY(ctx->pinned_acquire(job->h_out_bytes, &job->h_out));
     BB_CUDA(cudaMemcpyAsync(job->h_out, fin, pts, cudaMemcpyDeviceToHost, st));
     BB_CUDA(cudaMemcpyAsync((char*)job->h_out + pts, job->d_err.p, 16, cudaMemcpyDeviceToHost, st));
     ctx->d2h_bytes += pts + 16;
@@ -607,7 +669,7 @@ int msm_wait_result(bb_msm_job* job, MsmResult* res) {
         for (auto& e : job->ev) if (e) cudaEventDestroy(e);
         cudaGetLastError();
     }
-    if (job->h_out) cudaFreeHost(job->h_out);
+    if (job->h_out) job->ctx->pinned_release(job->h_out);
     delete job;
     return status;
 }

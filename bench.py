@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--cpu-sample-log", type=int, default=16, help="log2 constraints of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--window-bits", type=int, default=0)
+    ap.add_argument("--acc-variant", type=int, default=0)
     return ap.parse_args()
 
 
@@ -74,7 +75,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -329,6 +330,7 @@ def run_msm(args):
     worker = bb.Worker(0)
     if args.window_bits:
         worker.set_option("msm_window_bits", args.window_bits)
+    worker.set_option("msm_acc_variant", args.acc_variant)
     log("generating bases and scalars on the device")
     bases = bb.Bases.synthetic(worker, bb.G1, 31, n)
     d_sc = worker.device_alloc(n * 32)
@@ -336,12 +338,12 @@ def run_msm(args):
     log("inputs resident")
     worker.set_option("profile", 1)
     out = None
+    sampler = ClockSampler(0)
+    sampler.start()                  # before the warm-up: NVML start-up stalls driver calls for ~100 ms
     for _ in range(args.warmup):
         out = bb.multiexp_device(worker, (bases, 0), d_sc, n, bb.FORM_CANONICAL).wait()
     worker.synchronize()
     worker.profile_reset()
-    sampler = ClockSampler(0)
-    sampler.start()
     l0 = worker.kernel_launches
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -377,12 +379,12 @@ def run_ntt(args):
     bb.synth_scalars_device(worker, 41, n, d)
     v = np.zeros((n, 4), np.uint64)
     worker.download(d, v)
+    sampler = ClockSampler(0)
+    sampler.start()
     for _ in range(args.warmup):
         bb.ntt_device(worker, d, log_n, bb.NTT_FFT)
         bb.ntt_device(worker, d, log_n, bb.NTT_IFFT)
     worker.synchronize()
-    sampler = ClockSampler(0)
-    sampler.start()
     l0 = worker.kernel_launches
     t0 = time.perf_counter()
     for _ in range(args.steps):
