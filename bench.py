@@ -47,6 +47,14 @@ def parse():
 
 
 T0 = time.time()
+_REAL_STDOUT = None
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
 
 
 def log(msg):
@@ -156,7 +164,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "constraints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -315,7 +323,7 @@ def run_prove(args):
     else:
         line["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     worker.close()
     if world > 1:
         dist.destroy_process_group()
@@ -365,7 +373,7 @@ def run_msm(args):
                          "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                          "accumulate_ms": acc_ms / args.steps, "device_ms": tot_ms / args.steps, "algorithmic_bytes_per_pair": 128},
             "result_head": bytes(out[0, :2]).hex()}
-    print(json.dumps(line))
+    emit(line)
     worker.close()
 
 
@@ -405,13 +413,19 @@ def run_ntt(args):
             "gpu_launches": int(worker.kernel_launches - l0), "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_ntt_pass (all passes)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_point": 64}}
-    print(json.dumps(line))
+    emit(line)
     assert ok
     worker.close()
 
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: everything libraries print (NCCL banner, ...) goes
+    # to stderr until the result is ready
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "msm":
