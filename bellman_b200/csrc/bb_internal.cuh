@@ -54,6 +54,7 @@ struct bb_ctx {
     long opt_ntt_col_bits = 3;
     long opt_profile = 0;
     long opt_msm_acc_variant = 0;
+    long opt_msm_reduce_k = 8;
     struct ProfEntry { double ms = 0; uint64_t launches = 0, units = 0; };
     std::map<std::string, ProfEntry> prof;
     void prof_add(const char* what, double ms, uint64_t launches, uint64_t units) {

@@ -303,35 +303,63 @@ __global__ void __launch_bounds__(128) k_point_tree_sum(const XYZZ<F>* in, uint3
     if (threadIdx.x == 0) st_words(out + blockIdx.x, acc);
 }
 
-// Summation by parts (multiexp.rs:271-275) in parallel.  Window w = blockIdx.y; its D buckets
-// are cut into gridDim.x*blockDim.x runs of K; run j contributes
-//   sum_{t<K} (t+1) B[jK+t]  +  jK * sum_t B[jK+t].
+// Summation by parts (multiexp.rs:271-275) in parallel and without scalar multiplications.
+// A window's D buckets carry weights 1..D.  Thread j owns K adjacent entries and produces
+//   acc_j = sum_t (t + base) * in[jK+t]   (base = 1 on the first level, 0 afterwards)
+//   run_j = sum_t in[jK+t]
+// so that  sum_d w(d) in[d] = sum_j acc_j + K * sum_j j * run_j : the second term is the same
+// problem on the D/K run sums with 0-based weights.  Recursing until one run is left gives
+//   S = A_1 + K_1 (A_2 + K_2 (A_3 + ...)),   A_l = sum_j acc_j at level l,
+// two additions per bucket in total, every level fully parallel.
 template <class F>
-__global__ void __launch_bounds__(128) k_msm_reduce(const XYZZ<F>* buckets, uint32_t D, uint32_t K, XYZZ<F>* partials) {
+__global__ void __launch_bounds__(128) k_msm_reduce_level(const XYZZ<F>* in, uint32_t D_in, uint32_t K, int one_based,
+                                                          XYZZ<F>* run_out, XYZZ<F>* acc_partials) {
     extern __shared__ uint4 shraw[];
     XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(shraw);
     const uint32_t w = blockIdx.y;
+    const uint32_t runs = D_in / K;
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     XYZZ<F> acc = XYZZ<F>::identity();
-    if ((uint64_t)j * K < D) {
-        const XYZZ<F>* B = buckets + (size_t)w * D + (size_t)j * K;
+    if (j < runs) {
+        const XYZZ<F>* B = in + (size_t)w * D_in + (size_t)j * K;
         XYZZ<F> running = XYZZ<F>::identity();
-        for (int t = (int)K - 1; t >= 0; t--) {
+        for (int t = (int)K - 1; t >= 1; t--) {
             running.add(ld_words(B + t));
             acc.add(running);
         }
-        uint32_t m = j * K;                          // lift by the run's offset
-        if (m) {
-            XYZZ<F> lifted = XYZZ<F>::identity();
-            for (int bit = 31 - __clz(m); bit >= 0; bit--) {
-                lifted = lifted.dbl();
-                if ((m >> bit) & 1) lifted.add(running);
-            }
-            acc.add(lifted);
-        }
+        running.add(ld_words(B));
+        if (one_based) acc.add(running);
+        st_words(run_out + (size_t)w * runs + j, running);
     }
     block_tree_reduce(acc, sh);
-    if (threadIdx.x == 0) st_words(partials + (size_t)w * gridDim.x + blockIdx.x, acc);
+    if (threadIdx.x == 0) st_words(acc_partials + (size_t)w * gridDim.x + blockIdx.x, acc);
+}
+
+// S_w = A_1[w] + K_1 (A_2[w] + K_2 (A_3[w] + ...)); level sums are stored level-major: A[l*W + w]
+struct ReduceLevels { uint32_t n; uint32_t logk[12]; uint32_t nblk[12]; uint32_t part_off[12]; };
+
+// level_sums[l*W + w] = sum of the nblk[l] CTA partials of window w at level l; grid (W, levels)
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_level_sums(const XYZZ<F>* partials, uint32_t W, ReduceLevels L, XYZZ<F>* level_sums) {
+    extern __shared__ uint4 shraw[];
+    XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(shraw);
+    const uint32_t w = blockIdx.x, l = blockIdx.y, cnt = L.nblk[l];
+    const XYZZ<F>* in = partials + L.part_off[l] + (size_t)w * cnt;
+    XYZZ<F> acc = XYZZ<F>::identity();
+    for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) acc.add(ld_words(in + k));
+    block_tree_reduce(acc, sh);
+    if (threadIdx.x == 0) st_words(level_sums + (size_t)l * W + w, acc);
+}
+template <class F>
+__global__ void __launch_bounds__(32) k_msm_reduce_combine(const XYZZ<F>* level_sums, uint32_t W, ReduceLevels L, XYZZ<F>* out) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    XYZZ<F> s = ld_words(level_sums + (size_t)(L.n - 1) * W + w);
+    for (int l = (int)L.n - 2; l >= 0; l--) {
+        for (uint32_t k = 0; k < L.logk[l]; k++) s = s.dbl();
+        s.add(ld_words(level_sums + (size_t)l * W + w));
+    }
+    st_words(out + w, s);
 }
 
 // Error classification when BOTH an EOF and an identity base were seen: the reference folds
@@ -377,7 +405,7 @@ struct bb_msm_job {
     size_t n = 0;
     int status = BB_OK;              // pre-launch failure, reported at wait()
     DigitArgs dargs{};
-    DevBuf d_scalars, d_density, d_rank, d_counts, d_offsets, d_tiles, d_sorted, d_order, d_buckets, d_partials, d_final, d_ones, d_err;
+    DevBuf d_scalars, d_density, d_rank, d_counts, d_offsets, d_tiles, d_sorted, d_order, d_buckets, d_partials, d_runs, d_levels, d_onesp, d_final, d_ones, d_err;
     std::vector<uint32_t> h_rank;
     void* h_out = nullptr;           // pinned: [W window sums][1 ones sum] then err[4]
     size_t h_out_bytes = 0;
@@ -397,6 +425,60 @@ uint32_t choose_window(bb_ctx* ctx, size_t n) {
     if (n < (1u << 13)) return 8;
     if (n < (1u << 23)) return 16;
     return 20;
+}
+
+
+// Runs the multi-level bucket reduction for W windows of D buckets; window sums -> out[0..W)
+template <class F>
+int reduce_buckets(bb_ctx* ctx, cudaStream_t st, const XYZZ<F>* buckets, uint32_t W, uint32_t D, uint32_t K0,
+                   DevBuf& d_runs, DevBuf& d_partials, DevBuf& d_levels, XYZZ<F>* out) {
+    struct Level { uint32_t D_in, K, runs, nblk; };
+    std::vector<Level> lv;
+    for (uint32_t d = D;;) {
+        uint32_t K = K0 < d ? K0 : d;
+        uint32_t runs = d / K;
+        lv.push_back({d, K, runs, (runs + 127) / 128});
+        if (runs == 1) break;
+        d = runs;
+    }
+    if (lv.size() > 12) { set_error("bucket reduction: too many levels"); return BB_ERR_ARG; }
+    size_t run_total = 0, part_total = 0;
+    for (auto& l : lv) { run_total += (size_t)W * l.runs; part_total += (size_t)W * l.nblk; }
+    BB_TRY(d_runs.alloc(ctx, run_total * sizeof(XYZZ<F>)));
+    BB_TRY(d_partials.alloc(ctx, part_total * sizeof(XYZZ<F>)));
+    BB_TRY(d_levels.alloc(ctx, lv.size() * W * sizeof(XYZZ<F>)));
+    const size_t sh = 128 * sizeof(XYZZ<F>);
+    if (sh > 48 * 1024) {
+        BB_CUDA(cudaFuncSetAttribute(k_msm_reduce_level<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        BB_CUDA(cudaFuncSetAttribute(k_msm_level_sums<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        BB_CUDA(cudaFuncSetAttribute(k_point_tree_sum<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    }
+    const XYZZ<F>* in = buckets;
+    XYZZ<F>* runs = d_runs.as<XYZZ<F>>();
+    XYZZ<F>* parts = d_partials.as<XYZZ<F>>();
+    XYZZ<F>* levels = d_levels.as<XYZZ<F>>();
+    ReduceLevels RL{};
+    RL.n = (uint32_t)lv.size();
+    size_t part_off = 0;
+    for (size_t l = 0; l < lv.size(); l++) {
+        const Level& L = lv[l];
+        k_msm_reduce_level<F><<<dim3(L.nblk, W), 128, sh, st>>>(in, L.D_in, L.K, l == 0 ? 1 : 0, runs, parts + part_off);
+        ctx->count_launch();
+        uint32_t lg = 0;
+        while ((1u << lg) < L.K) lg++;
+        RL.logk[l] = lg;
+        RL.nblk[l] = L.nblk;
+        RL.part_off[l] = (uint32_t)part_off;
+        in = runs;
+        runs += (size_t)W * L.runs;
+        part_off += (size_t)W * L.nblk;
+    }
+    k_msm_level_sums<F><<<dim3(W, RL.n), 128, sh, st>>>(parts, W, RL, levels);
+    ctx->count_launch();
+    k_msm_reduce_combine<F><<<cdiv(W, 32), 32, 0, st>>>(levels, W, RL, out);
+    ctx->count_launch();
+    BB_CUDA(cudaGetLastError());
+    return BB_OK;
 }
 
 // BB_TRACE=1: synchronise after every stage and report it (debugging aid, off the hot path)
@@ -427,13 +509,7 @@ int launch_msm(bb_msm_job* job) {
     BB_TRY(job->d_err.alloc(ctx, 16));
     BB_TRY(job->d_buckets.alloc(ctx, NB * sizeof(XYZZ<F>)));
     BB_TRY(job->d_order.alloc(ctx, (NB + SIZE_BINS) * 4));
-    // reduction geometry: K buckets per thread, 128 threads per CTA
-    uint32_t K = 16;
-    while (K > 1 && (D / K) < 128) K >>= 1;
-    uint32_t runs = (D + K - 1) / K;
-    uint32_t nblk = (runs + 127) / 128;
     const uint32_t ONES_BLOCKS = 64;
-    BB_TRY(job->d_partials.alloc(ctx, ((size_t)W * nblk + ONES_BLOCKS) * sizeof(XYZZ<F>)));
     BB_TRY(job->d_final.alloc(ctx, (size_t)(W + 1) * sizeof(XYZZ<F>) + 16));
 
     BB_CUDA(cudaMemsetAsync(job->d_counts.p, 0, (NB + 1) * 4, st));
@@ -489,19 +565,15 @@ int launch_msm(bb_msm_job* job) {
     ctx->count_launch();
     if (prof) BB_CUDA(cudaEventRecord(job->ev[2], st));
     BB_STAGE("accumulate");
-    XYZZ<F>* partials = job->d_partials.as<XYZZ<F>>();
-    size_t sh = 128 * sizeof(XYZZ<F>);
-    if (sh > 48 * 1024) {
-        BB_CUDA(cudaFuncSetAttribute(k_msm_reduce<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-        BB_CUDA(cudaFuncSetAttribute(k_msm_sum_list<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-        BB_CUDA(cudaFuncSetAttribute(k_point_tree_sum<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-    }
-    k_msm_reduce<F><<<dim3(nblk, W), 128, sh, st>>>(buckets, D, K, partials);
-    k_msm_sum_list<F><<<ONES_BLOCKS, 128, sh, st>>>(bases, A.ones_list, A.ones_count, partials + (size_t)W * nblk, A.err);
     XYZZ<F>* fin = job->d_final.as<XYZZ<F>>();
-    k_point_tree_sum<F><<<W, 128, sh, st>>>(partials, nblk, fin);
-    k_point_tree_sum<F><<<1, 128, sh, st>>>(partials + (size_t)W * nblk, ONES_BLOCKS, fin + W);
-    ctx->count_launch(4);
+    BB_TRY(reduce_buckets<F>(ctx, st, buckets, W, D, (uint32_t)ctx->opt_msm_reduce_k, job->d_runs, job->d_partials, job->d_levels, fin));
+    size_t sh = 128 * sizeof(XYZZ<F>);
+    if (sh > 48 * 1024) BB_CUDA(cudaFuncSetAttribute(k_msm_sum_list<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    BB_TRY(job->d_onesp.alloc(ctx, ONES_BLOCKS * sizeof(XYZZ<F>)));
+    XYZZ<F>* ones_partials = job->d_onesp.as<XYZZ<F>>();
+    k_msm_sum_list<F><<<ONES_BLOCKS, 128, sh, st>>>(bases, A.ones_list, A.ones_count, ones_partials, A.err);
+    k_point_tree_sum<F><<<1, 128, sh, st>>>(ones_partials, ONES_BLOCKS, fin + W);
+    ctx->count_launch(2);
     BB_STAGE("reduce");
     BB_CUDA(cudaGetLastError());
     size_t pts = (size_t)(W + 1) * sizeof(XYZZ<F>);
@@ -702,16 +774,11 @@ int bb_selftest_bucket_reduce(bb_ctx* ctx, const void* affine_pts, uint32_t D, u
     std::vector<G1X> h(D);
     const G1Affine* a = (const G1Affine*)affine_pts;
     for (uint32_t i = 0; i < D; i++) h[i] = G1X::from_affine(a[i]);
-    uint32_t runs = (D + K - 1) / K, nblk = (runs + 127) / 128;
-    DevBuf d_b, d_p, d_f;
-    BB_TRY(d_b.alloc(ctx, D * sizeof(G1X))); BB_TRY(d_p.alloc(ctx, nblk * sizeof(G1X))); BB_TRY(d_f.alloc(ctx, sizeof(G1X)));
+    DevBuf d_b, d_p, d_r, d_l, d_f;
+    BB_TRY(d_b.alloc(ctx, D * sizeof(G1X))); BB_TRY(d_f.alloc(ctx, sizeof(G1X)));
     cudaStream_t st = ctx->main_stream;
     BB_CUDA(cudaMemcpyAsync(d_b.p, h.data(), D * sizeof(G1X), cudaMemcpyHostToDevice, st));
-    size_t sh = 128 * sizeof(G1X);
-    k_msm_reduce<Fp><<<dim3(nblk, 1), 128, sh, st>>>(d_b.as<G1X>(), D, K, d_p.as<G1X>());
-    k_point_tree_sum<Fp><<<1, 128, sh, st>>>(d_p.as<G1X>(), nblk, d_f.as<G1X>());
-    ctx->count_launch(2);
-    BB_CUDA(cudaGetLastError());
+    BB_TRY(reduce_buckets<Fp>(ctx, st, d_b.as<G1X>(), 1, D, K, d_r, d_p, d_l, d_f.as<G1X>()));
     G1X r;
     BB_CUDA(cudaMemcpyAsync(&r, d_f.p, sizeof r, cudaMemcpyDeviceToHost, st));
     BB_CUDA(cudaStreamSynchronize(st));

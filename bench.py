@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--acc-variant", type=int, default=0)
+    ap.add_argument("--reduce-k", type=int, default=0)
     return ap.parse_args()
 
 
@@ -59,6 +60,15 @@ def emit(line):
 
 def log(msg):
     print(f"[bench +{time.time() - T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+def measured_traffic():
+    """DRAM bytes per (base, scalar) pair of the dominant kernel from the committed ncu capture"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "roofline_r01.json")))
+        return float(d["traffic_bytes_per_pair"]), d["source"]
+    except Exception:
+        return None, None
 
 
 def peaks():
@@ -210,6 +220,8 @@ def run_prove(args):
     worker = bb.Worker(local)
     if args.window_bits:
         worker.set_option("msm_window_bits", args.window_bits)
+    if args.reduce_k:
+        worker.set_option("msm_reduce_k", args.reduce_k)
     log("synthesising the MiMC-chain witness (CPU, product-side generator)")
     asg, shape = bb.synth_mimc(rounds, seed=20, pinned=True)
     assert shape["num_constraints"] == 1 << log_n == shape["m"]
@@ -289,6 +301,8 @@ def run_prove(args):
     # scalars; each accumulates its base range)
     alg_bytes = 128.0 * acc_units / max(world, 1)
     achieved = alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None
+    tr_pair, tr_src = measured_traffic()
+    pairs_per_launch = acc_units / max(world, 1) / acc_launches if acc_launches else 0
     line = {
         "metric": METRIC, "value": value, "unit": "constraints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt_val / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -306,11 +320,17 @@ def run_prove(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate<Fp> (G1 bucket accumulation)", "achieved": achieved, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
+                     "traffic": (tr_pair * pairs_per_launch) if tr_pair else None, "traffic_source": tr_src,
+                     "algorithmic_bytes_per_launch": 128.0 * pairs_per_launch, "peak_source": peak_src,
                      "launches": int(acc_launches), "avg_launch_ms": acc_ms / acc_launches if acc_launches else None,
                      "algorithmic_bytes_per_pair": 128,
                      "share_of_step": (acc_ms / max(world, 1)) / (1e3 * dt_val) if dt_val else None,
                      "note": "integer-ALU bound, not HBM bound (SURVEY.md 8d): see integer_roofline",
+                     "integer_roofline": {"bound": "int32 multiplier", "unit": "G Fp-mul/s",
+                                          "achieved": (10.0 * 16 * acc_units / max(world, 1) / (acc_ms * 1e-3) / 1e9) if acc_ms > 0 else None,
+                                          "peak": 31.2, "peak_source": "profiles/ubench_r01.txt: 288 IMAD.WIDE-class products per Fp-mul at ~30/clk/SM",
+                                          "model": "10 Fp-mul per mixed addition x 16 windows per pair (an upper bound: zero digits are skipped)"},
                      "g2_accumulate_ms_per_step": acc2_ms / args.steps, "g1_msm_total_ms_per_step": tot_ms / args.steps},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -339,6 +359,8 @@ def run_msm(args):
     if args.window_bits:
         worker.set_option("msm_window_bits", args.window_bits)
     worker.set_option("msm_acc_variant", args.acc_variant)
+    if args.reduce_k:
+        worker.set_option("msm_reduce_k", args.reduce_k)
     log("generating bases and scalars on the device")
     bases = bb.Bases.synthetic(worker, bb.G1, 31, n)
     d_sc = worker.device_alloc(n * 32)

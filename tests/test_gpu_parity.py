@@ -89,6 +89,23 @@ def test_point_arithmetic(worker):
             assert bb.point_compress(group, pts[i:i + 1]) == bytes(comp[i])
 
 
+def test_bucket_reduction_kernels(worker):
+    """sum_d d * B_d (multiexp.rs:271-275) through the multi-level reduction, every level shape."""
+    lib = bb.load_library()
+    rng = random.Random(33)
+    for D, K in ((1, 8), (2, 8), (8, 8), (64, 2), (64, 8), (512, 16), (4096, 8), (4096, 4), (32768, 8)):
+        ks = [rng.randrange(R) for _ in range(D)]
+        for i in range(0, D, 7):
+            ks[i] = 0                                   # empty buckets
+        pts = o1.g1_fixed_mul(o1.fr_from_ints(ks))
+        out = np.zeros((1, 12), np.uint64)
+        rc = lib.bb_selftest_bucket_reduce(worker._h, pts.ctypes.data_as(C.c_void_p), C.c_uint32(D), C.c_uint32(K),
+                                           out.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        want = o1.g1_fixed_mul(o1.fr_from_ints([sum((i + 1) * k for i, k in enumerate(ks)) % R]))
+        assert np.array_equal(out, want), (D, K)
+
+
 # --------------------------------------------------------------------------------------------
 # NTT (src/domain.rs)
 # --------------------------------------------------------------------------------------------
