@@ -230,22 +230,34 @@ __global__ void __launch_bounds__(1024) k_size_scan(uint32_t* size_hist) {
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < SIZE_BINS; i += blockDim.x) size_hist[i] = sh[i];
 }
-__global__ void __launch_bounds__(256) k_size_order(const uint32_t* __restrict__ offsets, size_t nb, uint32_t* size_cursor, uint32_t* order) {
+// Oversized buckets (skewed scalars: a witness full of equal small values) are cut into tasks of
+// at most `cap` entries so that no single thread owns a long serial chain; big[0] counts tasks,
+// big[1] counts oversized buckets.
+struct BigTask { uint32_t bucket, begin, end; };
+struct BigBucket { uint32_t bucket, first_task, num_tasks; };
+
+__global__ void __launch_bounds__(256) k_size_order(const uint32_t* __restrict__ offsets, size_t nb, uint32_t* size_cursor, uint32_t* order,
+                                                     uint32_t cap, uint32_t* big, BigTask* tasks, BigBucket* big_list) {
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
-    uint32_t sz = offsets[b + 1] - offsets[b];
+    uint32_t start = offsets[b], end = offsets[b + 1];
+    uint32_t sz = end - start;
     order[atomicAdd(&size_cursor[sz < SIZE_BINS - 1 ? sz : SIZE_BINS - 1], 1u)] = (uint32_t)b;
+    if (sz > cap) {
+        uint32_t nt = (sz + cap - 1) / cap;
+        uint32_t first = atomicAdd(&big[0], nt);
+        big_list[atomicAdd(&big[1], 1u)] = {(uint32_t)b, first, nt};
+        for (uint32_t i = 0; i < nt; i++) {
+            uint32_t lo = start + i * cap, hi = lo + cap < end ? lo + cap : end;
+            tasks[first + i] = {(uint32_t)b, lo, hi};
+        }
+    }
 }
 
 // ---- bucket accumulation ------------------------------------------------------------------
-template <class F, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ offsets,
-                                                        const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ order,
-                                                        XYZZ<F>* buckets, size_t nb, uint32_t* err) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nb) return;
-    const uint32_t b = order[t];
-    uint32_t start = offsets[b], end = offsets[b + 1];
+template <class F>
+__device__ __forceinline__ XYZZ<F> accumulate_range(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                    uint32_t start, uint32_t end, uint32_t* err) {
     XYZZ<F> acc = XYZZ<F>::identity();
     for (uint32_t k = start; k < end; k++) {
         uint32_t v = sorted[k];
@@ -254,7 +266,33 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const Affine<F>* _
         if (v >> 31) p.y = p.y.neg();
         acc.add_mixed(p);
     }
+    return acc;
+}
+
+template <class F, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ offsets,
+                                                        const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ order,
+                                                        XYZZ<F>* buckets, size_t nb, uint32_t cap, uint32_t* err) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb) return;
+    const uint32_t b = order[t];
+    uint32_t start = offsets[b], end = offsets[b + 1];
+    if (end - start > cap) return;                                   // cut into tasks, see k_msm_accumulate_tasks
+    XYZZ<F> acc = accumulate_range<F>(bases, sorted, start, end, err);
     st_words(buckets + b, acc);
+}
+
+// one thread per task of an oversized bucket (grid-stride: the task count lives on the device)
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_accumulate_tasks(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                              const uint32_t* __restrict__ big, const BigTask* __restrict__ tasks,
+                                                              XYZZ<F>* task_sums, uint32_t* err) {
+    const uint32_t ntasks = big[0];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ntasks; t += gridDim.x * blockDim.x) {
+        BigTask tk = tasks[t];
+        XYZZ<F> acc = accumulate_range<F>(bases, sorted, tk.begin, tk.end, err);
+        st_words(task_sums + t, acc);
+    }
 }
 
 // sum of listed bases (scalar == 1): thread-strided partials then CTA tree
@@ -274,6 +312,23 @@ __device__ __forceinline__ void block_tree_reduce(XYZZ<F>& acc, XYZZ<F>* sh) {
         __syncthreads();
     }
     acc = ld_words(sh);
+}
+
+// bucket = sum of its task sums; one CTA per oversized bucket (grid-stride)
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_merge_big(const uint32_t* __restrict__ big, const BigBucket* __restrict__ big_list,
+                                                       const XYZZ<F>* task_sums, XYZZ<F>* buckets) {
+    extern __shared__ uint4 shraw[];
+    XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(shraw);
+    const uint32_t nbig = big[1];
+    for (uint32_t i = blockIdx.x; i < nbig; i += gridDim.x) {
+        BigBucket bb_ = big_list[i];
+        XYZZ<F> acc = XYZZ<F>::identity();
+        for (uint32_t k = threadIdx.x; k < bb_.num_tasks; k += blockDim.x) acc.add(ld_words(task_sums + bb_.first_task + k));
+        block_tree_reduce(acc, sh);
+        if (threadIdx.x == 0) st_words(buckets + bb_.bucket, acc);
+        __syncthreads();
+    }
 }
 
 template <class F>
@@ -405,7 +460,7 @@ struct bb_msm_job {
     size_t n = 0;
     int status = BB_OK;              // pre-launch failure, reported at wait()
     DigitArgs dargs{};
-    DevBuf d_scalars, d_density, d_rank, d_counts, d_offsets, d_tiles, d_sorted, d_order, d_buckets, d_partials, d_runs, d_levels, d_onesp, d_final, d_ones, d_err;
+    DevBuf d_scalars, d_density, d_rank, d_counts, d_offsets, d_tiles, d_sorted, d_order, d_buckets, d_partials, d_runs, d_levels, d_onesp, d_final, d_ones, d_err, d_big, d_tasks, d_biglist, d_tasksums;
     std::vector<uint32_t> h_rank;
     void* h_out = nullptr;           // pinned: [W window sums][1 ones sum] then err[4]
     size_t h_out_bytes = 0;
@@ -552,17 +607,41 @@ int launch_msm(bb_msm_job* job) {
     XYZZ<F>* buckets = job->d_buckets.as<XYZZ<F>>();
     uint32_t* order = job->d_order.as<uint32_t>();
     uint32_t* size_hist = order + NB;
+    // oversized-bucket threshold: 8x the mean bucket load, at least 256, and large enough that at
+    // most ~64K tasks exist
+    const uint64_t entries = (uint64_t)n * W;
+    uint64_t cap64 = 8 * ((entries + NB - 1) / NB);
+    if (cap64 < 256) cap64 = 256;
+    if (cap64 < (entries + 65535) / 65536) cap64 = (entries + 65535) / 65536;
+    if (ctx->opt_msm_big_cap > 0) cap64 = (uint64_t)ctx->opt_msm_big_cap;
+    const uint32_t cap = (uint32_t)cap64;
+    const size_t max_big = (size_t)(entries / cap) + 16, max_tasks = 2 * max_big;
+    BB_TRY(job->d_big.alloc(ctx, 16));
+    BB_TRY(job->d_tasks.alloc(ctx, max_tasks * sizeof(BigTask)));
+    BB_TRY(job->d_biglist.alloc(ctx, max_big * sizeof(BigBucket)));
+    BB_TRY(job->d_tasksums.alloc(ctx, max_tasks * sizeof(XYZZ<F>)));
+    uint32_t* big = job->d_big.as<uint32_t>();
+    BB_CUDA(cudaMemsetAsync(big, 0, 16, st));
     BB_CUDA(cudaMemsetAsync(size_hist, 0, SIZE_BINS * 4, st));
     k_size_hist<<<cdiv(NB, 256), 256, 0, st>>>(offsets, NB, size_hist);
     k_size_scan<<<1, 1024, 0, st>>>(size_hist);
-    k_size_order<<<cdiv(NB, 256), 256, 0, st>>>(offsets, NB, size_hist, order);
+    k_size_order<<<cdiv(NB, 256), 256, 0, st>>>(offsets, NB, size_hist, order, cap, big, job->d_tasks.as<BigTask>(), job->d_biglist.as<BigBucket>());
     ctx->count_launch(3);
     BB_STAGE("order");
+    const size_t sh_pt = 128 * sizeof(XYZZ<F>);
+    if (sh_pt > 48 * 1024) BB_CUDA(cudaFuncSetAttribute(k_msm_merge_big<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_pt));
     if (prof) BB_CUDA(cudaEventRecord(job->ev[1], st));
-    if (ctx->opt_msm_acc_variant == 1) k_msm_accumulate<F, 4><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, A.err);
-    else if (ctx->opt_msm_acc_variant == 2) k_msm_accumulate<F, 5><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, A.err);
-    else k_msm_accumulate<F, 1><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, A.err);
-    ctx->count_launch();
+    if (ctx->opt_msm_acc_variant == 1) k_msm_accumulate<F, 4><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
+    else if (ctx->opt_msm_acc_variant == 2) k_msm_accumulate<F, 5><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
+    else k_msm_accumulate<F, 1><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
+    {
+        unsigned tgrid = (unsigned)((max_tasks + 127) / 128);
+        if (tgrid > (unsigned)ctx->num_sms * 4) tgrid = (unsigned)ctx->num_sms * 4;
+        k_msm_accumulate_tasks<F><<<tgrid, 128, 0, st>>>(bases, A.sorted, big, job->d_tasks.as<BigTask>(), job->d_tasksums.as<XYZZ<F>>(), A.err);
+        unsigned mgrid = max_big < 1024 ? (unsigned)max_big : 1024u;
+        k_msm_merge_big<F><<<mgrid, 128, sh_pt, st>>>(big, job->d_biglist.as<BigBucket>(), job->d_tasksums.as<XYZZ<F>>(), buckets);
+    }
+    ctx->count_launch(3);
     if (prof) BB_CUDA(cudaEventRecord(job->ev[2], st));
     BB_STAGE("accumulate");
     XYZZ<F>* fin = job->d_final.as<XYZZ<F>>();

@@ -265,6 +265,37 @@ def test_multiexp_density_offset_and_fast_paths(worker):
     assert not got.any()                                           # P*k + P*(-k) = identity
 
 
+def test_multiexp_skewed_scalars(worker):
+    """Witnesses full of equal / tiny values put most bases into a handful of buckets; the
+    oversized-bucket path must give the same point (and not serialise on one thread)."""
+    rng = np.random.default_rng(8)
+    n = 6000
+    bases = o1.g1_fixed_mul(o1.fr_random(81, n))
+    cases = {
+        "all twos": o1.fr_from_ints([2] * n),
+        "nibbles": o1.fr_from_ints([int(x) for x in rng.integers(0, 16, n)]),
+        "bytes+big": o1.fr_from_ints([int(x) for x in rng.integers(0, 256, n - 5)] + [R - 1, R - 2, 3, 1 << 200, 7]),
+        "same 255-bit value": np.repeat(o1.fr_random(82, 1), n, axis=0),
+    }
+    for name, ex in cases.items():
+        rc, want = o1.multiexp(1, bases, 0, None, ex)
+        assert rc == 0
+        assert np.array_equal(_gpu_multiexp(worker, bb.G1, bases, 0, None, ex), want), name
+    # force the task path on ordinary data too: every bucket above 3 entries is cut up
+    ex = o1.fr_random(83, n)
+    rc, want = o1.multiexp(1, bases, 0, None, ex)
+    try:
+        worker.set_option("msm_big_cap", 3)
+        worker.set_option("msm_window_bits", 8)
+        assert np.array_equal(_gpu_multiexp(worker, bb.G1, bases, 0, None, ex), want)
+        b2 = o1.g2_fixed_mul(o1.fr_random(84, 500))
+        rc, want2 = o1.multiexp(2, b2, 0, None, ex[:500])
+        assert np.array_equal(_gpu_multiexp(worker, bb.G2, b2, 0, None, ex[:500]), want2)
+    finally:
+        worker.set_option("msm_big_cap", 0)
+        worker.set_option("msm_window_bits", 0)
+
+
 def test_multiexp_naive_property_full_size(worker):
     """benches/slow.rs shape scaled up (2^18 here; bench.py does 2^24): bases are [k_i]G made on
     the device, so the expected point is [sum k_i e_i]G -- multiexp.rs:334-378's property."""
