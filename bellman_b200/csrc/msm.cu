@@ -237,18 +237,18 @@ struct BigTask { uint32_t bucket, begin, end; };
 struct BigBucket { uint32_t bucket, first_task, num_tasks; };
 
 __global__ void __launch_bounds__(256) k_size_order(const uint32_t* __restrict__ offsets, size_t nb, uint32_t* size_cursor, uint32_t* order,
-                                                     uint32_t cap, uint32_t* big, BigTask* tasks, BigBucket* big_list) {
+                                                     uint32_t cap, uint32_t task_len, uint32_t* big, BigTask* tasks, BigBucket* big_list) {
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     uint32_t start = offsets[b], end = offsets[b + 1];
     uint32_t sz = end - start;
     order[atomicAdd(&size_cursor[sz < SIZE_BINS - 1 ? sz : SIZE_BINS - 1], 1u)] = (uint32_t)b;
     if (sz > cap) {
-        uint32_t nt = (sz + cap - 1) / cap;
+        uint32_t nt = (sz + task_len - 1) / task_len;
         uint32_t first = atomicAdd(&big[0], nt);
         big_list[atomicAdd(&big[1], 1u)] = {(uint32_t)b, first, nt};
         for (uint32_t i = 0; i < nt; i++) {
-            uint32_t lo = start + i * cap, hi = lo + cap < end ? lo + cap : end;
+            uint32_t lo = start + i * task_len, hi = lo + task_len < end ? lo + task_len : end;
             tasks[first + i] = {(uint32_t)b, lo, hi};
         }
     }
@@ -472,16 +472,18 @@ namespace {
 uint32_t choose_window(bb_ctx* ctx, size_t n) {
     if (ctx->opt_msm_window_bits >= 2 && ctx->opt_msm_window_bits <= 24) return (uint32_t)ctx->opt_msm_window_bits;
     // Signed-digit windows of c bits: W = floor(255/c)+1 windows, the top one holding only
-    // tb = 255 - (W-1)c scalar bits.  A top window with few bits has few live buckets, i.e.
-    // little parallelism for a thread-per-bucket accumulation (c = 14: 3 bits -> a handful of
-    // threads own n/8 additions each).  Only window sizes whose top window is (nearly) full
-    // are used: 4 (tb 3), 8 (tb 7), 16 (tb 15), 20 (tb 15).
+    // tb = 255 - (W-1)c scalar bits.  Measured on B200 (bench.py --workload msm --window-bits):
+    // n = 2^18: c=15 3.9 ms, c=16 4.2;  2^20: c=15 9.7, c=16 9.4, c=17 10.0;  2^22: c=16 30.1,
+    // c=17 29.5;  2^24: c=17 107.9, c=20 107.7.  Window sizes whose top window has only a few
+    // live buckets (c = 13, 14, 18, 19, 21: tb = 8, 3, 3, 8, 3) lose 1.5-3x even with the
+    // oversized-bucket path, so the choice is restricted to 8 (tb 7), 15 (tb 0: the top window is
+    // the carry alone, a single bucket that the task path sums as a tree), 16 (tb 15), 20 (tb 15).
     if (n < 32) return 4;
     if (n < (1u << 13)) return 8;
+    if (n < (1u << 19)) return 15;
     if (n < (1u << 23)) return 16;
     return 20;
 }
-
 
 // Runs the multi-level bucket reduction for W windows of D buckets; window sums -> out[0..W)
 template <class F>
@@ -607,15 +609,18 @@ int launch_msm(bb_msm_job* job) {
     XYZZ<F>* buckets = job->d_buckets.as<XYZZ<F>>();
     uint32_t* order = job->d_order.as<uint32_t>();
     uint32_t* size_hist = order + NB;
-    // oversized-bucket threshold: 8x the mean bucket load, at least 256, and large enough that at
-    // most ~64K tasks exist
+    // A bucket is oversized above 4x the mean load (at least 64 entries); it is cut into tasks of
+    // about the mean load (at least 32 entries, and few enough that <= ~256K tasks can exist), so
+    // the serial chain any thread owns stays short and the task sums are merged by a tree.
     const uint64_t entries = (uint64_t)n * W;
-    uint64_t cap64 = 8 * ((entries + NB - 1) / NB);
-    if (cap64 < 256) cap64 = 256;
-    if (cap64 < (entries + 65535) / 65536) cap64 = (entries + 65535) / 65536;
-    if (ctx->opt_msm_big_cap > 0) cap64 = (uint64_t)ctx->opt_msm_big_cap;
-    const uint32_t cap = (uint32_t)cap64;
-    const size_t max_big = (size_t)(entries / cap) + 16, max_tasks = 2 * max_big;
+    const uint64_t avg = (entries + NB - 1) / NB;
+    uint64_t cap64 = 4 * avg < 64 ? 64 : 4 * avg;
+    uint64_t len64 = avg < 32 ? 32 : avg;
+    if (len64 < (entries + 262143) / 262144) len64 = (entries + 262143) / 262144;
+    if (ctx->opt_msm_big_cap > 0) { cap64 = (uint64_t)ctx->opt_msm_big_cap; len64 = cap64; }
+    if (cap64 < len64) cap64 = len64;
+    const uint32_t cap = (uint32_t)cap64, task_len = (uint32_t)len64;
+    const size_t max_big = (size_t)(entries / cap) + 16, max_tasks = (size_t)(entries / task_len) + max_big + 16;
     BB_TRY(job->d_big.alloc(ctx, 16));
     BB_TRY(job->d_tasks.alloc(ctx, max_tasks * sizeof(BigTask)));
     BB_TRY(job->d_biglist.alloc(ctx, max_big * sizeof(BigBucket)));
@@ -625,7 +630,7 @@ int launch_msm(bb_msm_job* job) {
     BB_CUDA(cudaMemsetAsync(size_hist, 0, SIZE_BINS * 4, st));
     k_size_hist<<<cdiv(NB, 256), 256, 0, st>>>(offsets, NB, size_hist);
     k_size_scan<<<1, 1024, 0, st>>>(size_hist);
-    k_size_order<<<cdiv(NB, 256), 256, 0, st>>>(offsets, NB, size_hist, order, cap, big, job->d_tasks.as<BigTask>(), job->d_biglist.as<BigBucket>());
+    k_size_order<<<cdiv(NB, 256), 256, 0, st>>>(offsets, NB, size_hist, order, cap, task_len, big, job->d_tasks.as<BigTask>(), job->d_biglist.as<BigBucket>());
     ctx->count_launch(3);
     BB_STAGE("order");
     const size_t sh_pt = 128 * sizeof(XYZZ<F>);
@@ -683,7 +688,8 @@ int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint
         job->status = BB_ERR_DENSITY_MISMATCH;
         return BB_OK;
     }
-    job->c = choose_window(ctx, n);
+    // the pairs this device accumulates: all scalars on one GPU, about one shard's worth when sharded
+    job->c = choose_window(ctx, n < bases->n + 1 ? n : bases->n + 1);
     job->W = 255 / job->c + 1;
     job->D = 1u << (job->c - 1);
     auto fail = [&](int s) { job->status = s; return BB_OK; };
