@@ -55,6 +55,7 @@ struct bb_ctx {
     long opt_profile = 0;
     long opt_msm_acc_variant = 0;
     long opt_msm_reduce_k = 16;
+    long opt_msm_reduce_k1 = 16;
     long opt_msm_big_cap = 0;
     struct ProfEntry { double ms = 0; uint64_t launches = 0, units = 0; };
     std::map<std::string, ProfEntry> prof;

@@ -487,12 +487,13 @@ uint32_t choose_window(bb_ctx* ctx, size_t n) {
 
 // Runs the multi-level bucket reduction for W windows of D buckets; window sums -> out[0..W)
 template <class F>
-int reduce_buckets(bb_ctx* ctx, cudaStream_t st, const XYZZ<F>* buckets, uint32_t W, uint32_t D, uint32_t K0,
+int reduce_buckets(bb_ctx* ctx, cudaStream_t st, const XYZZ<F>* buckets, uint32_t W, uint32_t D, uint32_t K0, uint32_t K1,
                    DevBuf& d_runs, DevBuf& d_partials, DevBuf& d_levels, XYZZ<F>* out) {
     struct Level { uint32_t D_in, K, runs, nblk; };
     std::vector<Level> lv;
     for (uint32_t d = D;;) {
-        uint32_t K = K0 < d ? K0 : d;
+        uint32_t Kl = lv.empty() ? K1 : K0;
+        uint32_t K = Kl < d ? Kl : d;
         uint32_t runs = d / K;
         lv.push_back({d, K, runs, (runs + 127) / 128});
         if (runs == 1) break;
@@ -610,13 +611,13 @@ int launch_msm(bb_msm_job* job) {
     uint32_t* order = job->d_order.as<uint32_t>();
     uint32_t* size_hist = order + NB;
     // A bucket is oversized above 4x the mean load (at least 64 entries); it is cut into tasks of
-    // about the mean load (at least 32 entries, and few enough that <= ~256K tasks can exist), so
+    // about the mean load (at least 32 entries, and few enough that <= ~1M tasks can exist), so
     // the serial chain any thread owns stays short and the task sums are merged by a tree.
     const uint64_t entries = (uint64_t)n * W;
     const uint64_t avg = (entries + NB - 1) / NB;
     uint64_t cap64 = 4 * avg < 64 ? 64 : 4 * avg;
     uint64_t len64 = avg < 32 ? 32 : avg;
-    if (len64 < (entries + 262143) / 262144) len64 = (entries + 262143) / 262144;
+    if (len64 < (entries + 1048575) / 1048576) len64 = (entries + 1048575) / 1048576;
     if (ctx->opt_msm_big_cap > 0) { cap64 = (uint64_t)ctx->opt_msm_big_cap; len64 = cap64; }
     if (cap64 < len64) cap64 = len64;
     const uint32_t cap = (uint32_t)cap64, task_len = (uint32_t)len64;
@@ -650,7 +651,7 @@ int launch_msm(bb_msm_job* job) {
     if (prof) BB_CUDA(cudaEventRecord(job->ev[2], st));
     BB_STAGE("accumulate");
     XYZZ<F>* fin = job->d_final.as<XYZZ<F>>();
-    BB_TRY(reduce_buckets<F>(ctx, st, buckets, W, D, (uint32_t)ctx->opt_msm_reduce_k, job->d_runs, job->d_partials, job->d_levels, fin));
+    BB_TRY(reduce_buckets<F>(ctx, st, buckets, W, D, (uint32_t)ctx->opt_msm_reduce_k, (uint32_t)ctx->opt_msm_reduce_k1, job->d_runs, job->d_partials, job->d_levels, fin));
     size_t sh = 128 * sizeof(XYZZ<F>);
     if (sh > 48 * 1024) BB_CUDA(cudaFuncSetAttribute(k_msm_sum_list<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
     BB_TRY(job->d_onesp.alloc(ctx, ONES_BLOCKS * sizeof(XYZZ<F>)));
@@ -863,7 +864,7 @@ int bb_selftest_bucket_reduce(bb_ctx* ctx, const void* affine_pts, uint32_t D, u
     BB_TRY(d_b.alloc(ctx, D * sizeof(G1X))); BB_TRY(d_f.alloc(ctx, sizeof(G1X)));
     cudaStream_t st = ctx->main_stream;
     BB_CUDA(cudaMemcpyAsync(d_b.p, h.data(), D * sizeof(G1X), cudaMemcpyHostToDevice, st));
-    BB_TRY(reduce_buckets<Fp>(ctx, st, d_b.as<G1X>(), 1, D, K, d_r, d_p, d_l, d_f.as<G1X>()));
+    BB_TRY(reduce_buckets<Fp>(ctx, st, d_b.as<G1X>(), 1, D, K, K, d_r, d_p, d_l, d_f.as<G1X>()));
     G1X r;
     BB_CUDA(cudaMemcpyAsync(&r, d_f.p, sizeof r, cudaMemcpyDeviceToHost, st));
     BB_CUDA(cudaStreamSynchronize(st));

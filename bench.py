@@ -44,6 +44,10 @@ def parse():
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--acc-variant", type=int, default=0)
     ap.add_argument("--reduce-k", type=int, default=0)
+    ap.add_argument("--reduce-k1", type=int, default=0)
+    ap.add_argument("--witness", default="uniform", choices=["uniform", "boolean"],
+                    help="boolean: every second aux value is overwritten with 0/1 (SURVEY.md 8d config 2's boolean-heavy variant; "
+                         "exercises the Exponent::Zero/One fast paths; no longer a satisfying assignment)")
     return ap.parse_args()
 
 
@@ -222,9 +226,15 @@ def run_prove(args):
         worker.set_option("msm_window_bits", args.window_bits)
     if args.reduce_k:
         worker.set_option("msm_reduce_k", args.reduce_k)
+    if args.reduce_k1:
+        worker.set_option("msm_reduce_k1", args.reduce_k1)
     log("synthesising the MiMC-chain witness (CPU, product-side generator)")
     asg, shape = bb.synth_mimc(rounds, seed=20, pinned=True)
     assert shape["num_constraints"] == 1 << log_n == shape["m"]
+    if args.witness == "boolean":
+        one = np.array([0x00000001fffffffe, 0x5884b7fa00034802, 0x998c4fefecbc4ff5, 0x1824b159acc5056f], dtype=np.uint64)  # R mod r
+        asg.aux_assignment[1::4] = 0
+        asg.aux_assignment[3::4] = one
     log("generating the synthetic CRS on the device")
     params = bb.Parameters.synthetic(worker, 21, shape, shard_index=rank, shard_count=world)
     log("CRS resident")
@@ -262,6 +272,7 @@ def run_prove(args):
         for _ in range(warmup):
             proof = step(device_ptrs)
         sync()
+        worker.profile_reset()
         l0 = worker.kernel_launches
         h0, d0 = worker.bytes_copied()
         t0 = time.perf_counter()
@@ -307,7 +318,8 @@ def run_prove(args):
         "metric": METRIC, "value": value, "unit": "constraints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt_val / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32 limbs (381-bit Fp / 255-bit Fr Montgomery integers)", "data": "synthetic",
-        "config": {"workload": f"groth16-prove-2^{log_n}-mimc-chain", "constraints": n_constraints, "num_aux": shape["num_aux"],
+        "config": {"workload": f"groth16-prove-2^{log_n}-mimc-chain" + ("-boolean-heavy" if args.witness == "boolean" else ""),
+                   "constraints": n_constraints, "num_aux": shape["num_aux"],
                    "msm_sizes": {"h": shape["m"] - 1, "l": shape["num_aux"], "a": shape["a_aux_total"] + 2, "b_g1": shape["b_aux_total"] + 1,
                                  "b_g2": shape["b_aux_total"] + 1},
                    "ntts": "7 x 2^%d" % log_n, "parallelism": f"msm-base-range-shards x{world}, NTT replicated",
