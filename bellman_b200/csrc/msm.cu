@@ -778,24 +778,6 @@ int msm_wait_result(bb_msm_job* job, MsmResult* res) {
     }
     if (status == BB_OK) {
         bool g2 = job->group == BB_G2;
-        if (getenv("BB_DEBUG_MSM") && !g2) {
-            size_t NB = (size_t)job->W * job->D;
-            std::vector<uint32_t> off(NB + 1), srt(job->n * job->W + 1);
-            cudaMemcpy(off.data(), job->d_offsets.p, (NB + 1) * 4, cudaMemcpyDeviceToHost);
-            cudaMemcpy(srt.data(), job->d_sorted.p, job->n * job->W * 4, cudaMemcpyDeviceToHost);
-            std::vector<G1X> bk(NB);
-            cudaMemcpy(bk.data(), job->d_buckets.p, NB * sizeof(G1X), cudaMemcpyDeviceToHost);
-            fprintf(stderr, "[msm dbg] n=%zu c=%u W=%u D=%u total=%u\n", job->n, job->c, job->W, job->D, off[NB]);
-            for (size_t b = 0; b < NB; b++) {
-                if (off[b + 1] != off[b]) fprintf(stderr, "  bucket %zu: [%u,%u) first=%08x  acc.X0=%08x ZZ0=%08x\n", b, off[b], off[b + 1], srt[off[b]], bk[b].X.l[0], bk[b].ZZ.l[0]);
-                else if (!bk[b].is_identity()) fprintf(stderr, "  bucket %zu EMPTY but non-identity\n", b);
-            }
-            const G1X* win = (const G1X*)job->h_out;
-            for (uint32_t w = 0; w <= job->W; w++) if (!win[w].is_identity()) {
-                G1Affine a = win[w].to_affine();
-                fprintf(stderr, "  window %u sum affine x0=%08x%08x\n", w, a.x.l[1], a.x.l[0]);
-            }
-        }
         size_t pts = (size_t)(job->W + 1) * (g2 ? sizeof(G2X) : sizeof(G1X));
         const uint32_t* err = (const uint32_t*)((char*)job->h_out + pts);
         bool eof = err[0] != 0xffffffffu, ident = err[1] != 0;
@@ -868,16 +850,6 @@ int bb_selftest_bucket_reduce(bb_ctx* ctx, const void* affine_pts, uint32_t D, u
     G1X r;
     BB_CUDA(cudaMemcpyAsync(&r, d_f.p, sizeof r, cudaMemcpyDeviceToHost, st));
     BB_CUDA(cudaStreamSynchronize(st));
-    if (getenv("BB_DEBUG_MSM")) {
-        G1X p0;
-        cudaMemcpy(&p0, d_p.p, sizeof p0, cudaMemcpyDeviceToHost);
-        auto dump = [](const char* nm, const G1X& v) {
-            fprintf(stderr, "%s X=%08x.. %08x Y=%08x.. ZZ=%08x..%08x ZZZ=%08x..%08x\n", nm, v.X.l[0], v.X.l[11], v.Y.l[0], v.ZZ.l[0], v.ZZ.l[11], v.ZZZ.l[0], v.ZZZ.l[11]);
-        };
-        dump("in[0]   ", h[0]);
-        dump("partial0", p0);
-        dump("final   ", r);
-    }
     G1Affine ra = r.to_affine();
     std::memcpy(out_affine, &ra, sizeof ra);
     return BB_OK;

@@ -356,6 +356,15 @@ def test_prove_mimc322_matches_oracle(worker):
         assert len(proof) == 192                                     # groth16/src/lib.rs:559
         assert proof == mc.prove(r, s)
         assert proof == mc.expected_proof(r, s)
+    # "the proof verifies under the reference verifier": Proof::read + verify_proof
+    # (groth16/src/lib.rs:47-99, verifier.rs:23-58) over the oracle's pairing
+    from oracle.oracle0 import pairing as PR
+    p = mc.export_params()
+    g1, g2 = o1.g1_to_affine_ints(p["vk_g1"]), o1.g2_to_affine_ints(p["vk_g2"])
+    vk = dict(alpha_g1=g1[0], beta_g2=g2[0], gamma_g2=g2[1], delta_g2=g2[2], ic=o1.g1_to_affine_ints(p["ic"]))
+    image = o1.fr_to_ints(mc.witness()["inputs"])[1]
+    assert PR.verify_proof(vk, PR.proof_read(proof), [image])
+    assert not PR.verify_proof(vk, PR.proof_read(proof), [image ^ 1])
     # sharded across "devices": partial sums from each base range add up to the same proof
     parts = []
     for k in range(3):
