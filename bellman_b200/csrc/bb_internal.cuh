@@ -57,6 +57,7 @@ struct bb_ctx {
     long opt_msm_reduce_k = 16;
     long opt_msm_reduce_k1 = 16;
     long opt_msm_big_cap = 0;
+    long opt_shard_windows = 4;      // multi-GPU: up to this many window shards per base range (1 = base ranges only)
     struct ProfEntry { double ms = 0; uint64_t launches = 0, units = 0; };
     std::map<std::string, ProfEntry> prof;
     void prof_add(const char* what, double ms, uint64_t launches, uint64_t units) {
@@ -85,6 +86,8 @@ struct bb_bases {
     size_t n;                // points held here
     size_t global_offset;    // first global index held
     size_t global_len;       // length of the whole (unsharded) vector
+    uint32_t win_index = 0;  // window shard: this device accumulates windows w % win_count == win_index
+    uint32_t win_count = 1;
 };
 
 namespace bb {

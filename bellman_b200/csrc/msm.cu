@@ -78,6 +78,7 @@ struct DigitArgs {
     uint64_t shard_lo, shard_n;     // this device holds global base indices [shard_lo, shard_lo+shard_n)
     uint64_t global_len;
     uint32_t c, W;
+    uint32_t win_index, win_count;  // this device owns windows w with w % win_count == win_index
     uint32_t* counts;               // mode 0: histogram; mode 1: cursors
     uint32_t* sorted;               // mode 1
     uint32_t* ones_list;            // base indices with scalar == 1
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(DigitArgs A) {
     uint32_t local = (uint32_t)(gi - A.shard_lo);
     uint32_t rest = s.l[1] | s.l[2] | s.l[3] | s.l[4] | s.l[5] | s.l[6] | s.l[7];
     if (rest == 0 && s.l[0] == 1) {                                  // Exponent::One, :246-252
-        if (A.mode == 1) A.ones_list[atomicAdd(A.ones_count, 1u)] = local;
+        if (A.mode == 1 && A.win_index == 0) A.ones_list[atomicAdd(A.ones_count, 1u)] = local;   // window 0's owner
         return;
     }
     const uint32_t D = 1u << (A.c - 1);
@@ -129,8 +130,8 @@ __global__ void __launch_bounds__(256) k_msm_digits(DigitArgs A) {
         uint32_t mag, neg;
         if (raw > D) { mag = (1u << A.c) - raw; neg = 1; carry = 1; }
         else { mag = raw; neg = 0; carry = 0; }
-        if (mag == 0) continue;
-        uint32_t key = w * D + (mag - 1);
+        if (mag == 0 || w % A.win_count != A.win_index) continue;   // the carry chain runs over all windows
+        uint32_t key = (w / A.win_count) * D + (mag - 1);
         if (A.mode == 0) atomicAdd(&A.counts[key], 1u);
         else A.sorted[atomicAdd(&A.counts[key], 1u)] = local | (neg << 31);
     }
@@ -456,7 +457,8 @@ struct bb_msm_job {
     const bb_bases* bases = nullptr;
     cudaStream_t st = nullptr;
     int group = BB_G1;
-    uint32_t c = 0, W = 0, D = 0;
+    uint32_t c = 0, W = 0, D = 0;   // W = windows of the whole scalar
+    uint32_t W_local = 0;            // windows this device owns (all of them unless window-sharded)
     size_t n = 0;
     int status = BB_OK;              // pre-launch failure, reported at wait()
     DigitArgs dargs{};
@@ -555,7 +557,7 @@ template <class F>
 int launch_msm(bb_msm_job* job) {
     bb_ctx* ctx = job->ctx;
     cudaStream_t st = job->st;
-    const uint32_t W = job->W, D = job->D;
+    const uint32_t W = job->W_local, D = job->D;   // everything below works on the owned windows only
     const size_t NB = (size_t)W * D;
     const size_t n = job->n;
     BB_TRY(job->d_counts.alloc(ctx, (NB + 1) * 4));
@@ -699,6 +701,11 @@ int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint
     A.base_offset = base_offset;
     A.shard_lo = bases->global_offset; A.shard_n = bases->n; A.global_len = bases->global_len;
     A.c = job->c; A.W = job->W;
+    A.win_index = bases->win_index; A.win_count = bases->win_count ? bases->win_count : 1;
+    if (A.win_index >= A.win_count) { set_error("bb_msm: window shard %u of %u", A.win_index, A.win_count); return fail(BB_ERR_ARG); }
+    job->W_local = 0;
+    for (uint32_t w = 0; w < job->W; w++) job->W_local += (w % A.win_count == A.win_index);
+    if (job->W_local == 0) job->W_local = 1;          // degenerate: more shards than windows; slot stays empty
     int s;
     if (scalars_on_device) A.scalars = (const Fr*)scalars;
     else {
@@ -737,15 +744,18 @@ int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint
 
 }  // namespace bb
 namespace {
-// Horner fold over the window sums (multiexp.rs:295-300) plus the Exponent::One sum
+// Horner fold over the window sums (multiexp.rs:295-300) plus the Exponent::One sum.  `win` holds
+// the W_local windows this device owns (window w lives in slot w / wc when w % wc == wi), then the
+// ones sum; windows owned elsewhere contribute the identity here and are added by their owners'
+// partial results (the fold is linear).
 template <class F>
-XYZZ<F> fold_windows(const XYZZ<F>* win, uint32_t W, uint32_t c) {
+XYZZ<F> fold_windows(const XYZZ<F>* win, uint32_t W, uint32_t W_local, uint32_t c, uint32_t wi, uint32_t wc) {
     XYZZ<F> acc = XYZZ<F>::identity();
     for (int w = (int)W - 1; w >= 0; w--) {
         for (uint32_t k = 0; k < c; k++) acc = acc.dbl();
-        acc.add(win[w]);
+        if ((uint32_t)w % wc == wi && (uint32_t)w / wc < W_local) acc.add(win[(uint32_t)w / wc]);
     }
-    acc.add(win[W]);
+    acc.add(win[W_local]);
     return acc;
 }
 
@@ -778,7 +788,7 @@ int msm_wait_result(bb_msm_job* job, MsmResult* res) {
     }
     if (status == BB_OK) {
         bool g2 = job->group == BB_G2;
-        size_t pts = (size_t)(job->W + 1) * (g2 ? sizeof(G2X) : sizeof(G1X));
+        size_t pts = (size_t)(job->W_local + 1) * (g2 ? sizeof(G2X) : sizeof(G1X));
         const uint32_t* err = (const uint32_t*)((char*)job->h_out + pts);
         bool eof = err[0] != 0xffffffffu, ident = err[1] != 0;
         if (eof && ident) {
@@ -793,8 +803,9 @@ int msm_wait_result(bb_msm_job* job, MsmResult* res) {
         if (status == BB_ERR_UNEXPECTED_IDENTITY) set_error("encountered an identity element in the CRS");
         if (status == BB_OK) {
             res->g2 = g2;
-            if (g2) res->x2 = fold_windows<Fp2>((const G2X*)job->h_out, job->W, job->c);
-            else res->g1 = fold_windows<Fp>((const G1X*)job->h_out, job->W, job->c);
+            const uint32_t wi = job->dargs.win_index, wc = job->dargs.win_count;
+            if (g2) res->x2 = fold_windows<Fp2>((const G2X*)job->h_out, job->W, job->W_local, job->c, wi, wc);
+            else res->g1 = fold_windows<Fp>((const G1X*)job->h_out, job->W, job->W_local, job->c, wi, wc);
         }
     }
     res->status = status;

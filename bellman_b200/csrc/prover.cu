@@ -15,6 +15,17 @@ struct bb_crs {
 
 namespace {
 
+// Shard `idx` of `cnt` -> (base range b of nb) x (window shard v of nv).  Any partition of the
+// (base, window) pairs of an MSM folds to the same point, so the shards split the windows first
+// (that also divides the per-window bucket reduction, which base ranges alone do not) and the
+// base vector second: nv = the largest divisor of cnt not above ctx->opt_shard_windows (4),
+// nb = cnt / nv.  8 GPUs: 2 base ranges x 4 window shards.
+void shard_policy(const bb_ctx* ctx, uint32_t idx, uint32_t cnt, uint32_t* b, uint32_t* nb, uint32_t* v, uint32_t* nv) {
+    uint32_t lim = (uint32_t)(ctx->opt_shard_windows < 1 ? 1 : ctx->opt_shard_windows), w = 1;
+    for (uint32_t d = 1; d <= lim && d <= cnt; d++) if (cnt % d == 0) w = d;
+    *nv = w; *nb = cnt / w; *v = idx % w; *b = idx / w;
+}
+
 template <class F>
 bool affine_equal(const Affine<F>& a, const Affine<F>& b) { return a.x == b.x && a.y == b.y; }
 
@@ -86,10 +97,14 @@ int bb_crs_create(bb_ctx* ctx, const bb_crs_desc* d, bb_crs** out) {
     std::memcpy(&crs->alpha_g1, d->alpha_g1, 96); std::memcpy(&crs->beta_g1, d->beta_g1, 96);
     std::memcpy(&crs->delta_g1, d->delta_g1, 96);
     std::memcpy(&crs->beta_g2, d->beta_g2, 192); std::memcpy(&crs->delta_g2, d->delta_g2, 192);
+    uint32_t sb, snb, sv, snv;
+    shard_policy(ctx, idx, cnt, &sb, &snb, &sv, &snv);
     auto up = [&](int group, const void* pts, size_t len, bb_bases** dst) -> int {
-        size_t lo = len * idx / cnt, hi = len * (idx + 1) / cnt;
+        size_t lo = len * sb / snb, hi = len * (sb + 1) / snb;
         size_t stride = group == BB_G1 ? 96 : 192;
-        return bb_bases_upload(ctx, group, (const char*)pts + lo * stride, hi - lo, lo, len, dst);
+        int rc = bb_bases_upload(ctx, group, (const char*)pts + lo * stride, hi - lo, lo, len, dst);
+        if (rc == BB_OK) { (*dst)->win_index = sv; (*dst)->win_count = snv; }
+        return rc;
     };
     int s;
     if ((s = up(BB_G1, d->h, d->h_len, &crs->h)) || (s = up(BB_G1, d->l, d->l_len, &crs->l)) ||
@@ -118,9 +133,13 @@ int bb_synth_crs(bb_ctx* ctx, uint64_t seed, size_t h_len, size_t l_len, size_t 
     if (s == BB_OK) s = bb_fixed_base_mul(ctx, BB_G2, k2, 2, BB_FORM_CANONICAL, v2);
     crs->alpha_g1 = v1[0]; crs->beta_g1 = v1[1]; crs->delta_g1 = v1[2];
     crs->beta_g2 = v2[0]; crs->delta_g2 = v2[1];
+    uint32_t sb, snb, sv, snv;
+    shard_policy(ctx, shard_index, shard_count, &sb, &snb, &sv, &snv);
     auto gen = [&](int group, uint64_t sd, size_t len, bb_bases** dst) -> int {
-        size_t lo = len * shard_index / shard_count, hi = len * (shard_index + 1) / shard_count;
-        return bb_synth_bases(ctx, group, sd, hi - lo, lo, len, dst);
+        size_t lo = len * sb / snb, hi = len * (sb + 1) / snb;
+        int rc = bb_synth_bases(ctx, group, sd, hi - lo, lo, len, dst);
+        if (rc == BB_OK) { (*dst)->win_index = sv; (*dst)->win_count = snv; }
+        return rc;
     };
     if (s == BB_OK) s = gen(BB_G1, seed + 1, h_len, &crs->h);
     if (s == BB_OK) s = gen(BB_G1, seed + 2, l_len, &crs->l);

@@ -7,8 +7,9 @@ from . import PARTIALS_BYTES
 
 
 def shard_range(length, index, count):
-    """Contiguous base range of shard `index` of `count` -- the same split bb_crs_create uses
-    (bellman_b200/csrc/prover.cu): [length*index/count, length*(index+1)/count)."""
+    """Contiguous range `index` of `count` over `length` items:
+    [length*index/count, length*(index+1)/count) -- the split bb_crs_create applies to the base
+    vectors (after it has set aside up to 4 window groups, see prover.cu: shard_policy)."""
     return length * index // count, length * (index + 1) // count
 
 

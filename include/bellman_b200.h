@@ -145,9 +145,12 @@ typedef struct bb_crs_desc {
     const void* a;    size_t a_len;
     const void* b_g1; size_t b_g1_len;
     const void* b_g2; size_t b_g2_len;
-    /* multi-GPU: this process holds shard `shard_index` of `shard_count` contiguous base
-     * ranges of every vector above (the arrays passed are still the full vectors; the
-     * library uploads only its range).  Single GPU: 0 / 1. */
+    /* multi-GPU: this process is shard `shard_index` of `shard_count`.  A shard is a contiguous
+     * base range of every vector above, crossed with a subset of the MSM windows (any partition
+     * of the (base, window) pairs folds to the same point): the library splits the windows into
+     * up to 4 groups first and the base vectors second -- 8 shards = 2 base ranges x 4 window
+     * groups; bb_ctx_set_option(ctx, "shard_windows", 1) gives base ranges alone.  The arrays
+     * passed are the full vectors; only this shard's base range is uploaded.  Single GPU: 0 / 1. */
     uint32_t shard_index; uint32_t shard_count;
 } bb_crs_desc;
 

@@ -365,12 +365,26 @@ def test_prove_mimc322_matches_oracle(worker):
     image = o1.fr_to_ints(mc.witness()["inputs"])[1]
     assert PR.verify_proof(vk, PR.proof_read(proof), [image])
     assert not PR.verify_proof(vk, PR.proof_read(proof), [image ^ 1])
-    # sharded across "devices": partial sums from each base range add up to the same proof
-    parts = []
-    for k in range(3):
-        pk = bb.Parameters(worker, mc.export_params(), shard_index=k, shard_count=3)
-        parts.append(bb.prove_partials(asg, pk))
-    assert bb.finalize(params, parts, r, s) == proof
+    # sharded across "devices": the partial sums of the (base range x window) shards add up to the
+    # same proof.  2 and 3 shards split the windows only; 8 = 2 base ranges x 4 window shards;
+    # 5 has no divisor <= 4 and splits the bases only; shard_windows=1 forces base ranges alone.
+    for count in (2, 3, 5, 8):
+        parts = []
+        for k in range(count):
+            pk = bb.Parameters(worker, mc.export_params(), shard_index=k, shard_count=count)
+            parts.append(bb.prove_partials(asg, pk))
+            pk.free()
+        assert bb.finalize(params, parts, r, s) == proof, count
+    try:
+        worker.set_option("shard_windows", 1)
+        parts = []
+        for k in range(4):
+            pk = bb.Parameters(worker, mc.export_params(), shard_index=k, shard_count=4)
+            parts.append(bb.prove_partials(asg, pk))
+            pk.free()
+        assert bb.finalize(params, parts, r, s) == proof
+    finally:
+        worker.set_option("shard_windows", 4)
 
 
 def _manufacture_crs(worker, mc):
