@@ -252,7 +252,7 @@ void bb_ctx_destroy(bb_ctx* ctx) {
     for (auto p : ctx->pinned_free) cudaFreeHost(p);
     for (auto s : ctx->streams) cudaStreamDestroy(s);
     if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
-    // NTT tables are freed with the process; they are keyed by size and shared
+    ntt_free_tables(ctx);
     delete ctx;
 }
 
@@ -441,6 +441,30 @@ int bb_point_compress(int group, const void* a, uint8_t* out) {
     if (group == BB_G1) { G1Affine p; std::memcpy(&p, a, 96); g1_compress(p, out); }
     else if (group == BB_G2) { G2Affine p; std::memcpy(&p, a, 192); g2_compress(p, out); }
     else return BB_ERR_ARG;
+    return BB_OK;
+}
+// In-place conversion of n Fp coordinates (6 x u64 each) between canonical integers and the
+// Montgomery form the ABI uses; host code (parameter files: groth16/src/lib.rs:258-398 stores
+// canonical big-endian coordinates).
+int bb_fp_convert(void* fp_inout, size_t n, int to_montgomery) {
+    if (n && !fp_inout) return BB_ERR_ARG;
+    Fp* v = (Fp*)fp_inout;
+    for (size_t i = 0; i < n; i++) {
+        Fp x;
+        std::memcpy(&x, v + i, sizeof x);
+        if (to_montgomery) {
+            bool lt = false;                       // must be < p
+            for (int k = 11; k >= 0; k--) {
+                if (x.l[k] < bbc::FP_MOD[k]) { lt = true; break; }
+                if (x.l[k] > bbc::FP_MOD[k]) break;
+            }
+            if (!lt) { set_error("coordinate %zu is not a canonical field element", i); return BB_ERR_ARG; }
+            x = fp_from_canonical(x);
+        } else {
+            x = fp_to_canonical(x);
+        }
+        std::memcpy(v + i, &x, sizeof x);
+    }
     return BB_OK;
 }
 int bb_fixed_base_mul(bb_ctx* ctx, int group, const void* scalars, size_t n, int form, void* out) {

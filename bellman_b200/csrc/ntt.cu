@@ -324,6 +324,17 @@ int h_poly_device(bb_ctx* ctx, cudaStream_t st, Fr* d_a, Fr* d_b, Fr* d_c, Fr* d
     return run_passes(ctx, st, d_a, d_a, d_tmp, log_m, tw_i, fin);
 }
 
+void ntt_free_tables(bb_ctx* ctx) {
+    for (auto& kv : ctx->ntt_tables) {
+        NttTables* t = kv.second;
+        if (!t) continue;
+        Fr* ptrs[] = {t->tw_fwd, t->tw_inv, t->pow_g, t->pow_ginv_minv, t->pow_g_minv, t->pow_ginv_minv_zinv};
+        for (Fr* p : ptrs) if (p) cudaFree(p);
+        delete t;
+    }
+    ctx->ntt_tables.clear();
+}
+
 int fr_convert_device(bb_ctx* ctx, cudaStream_t st, Fr* d_data, size_t n, bool to_montgomery) {
     if (!n) return BB_OK;
     k_fr_convert<<<cdiv(n, 256), 256, 0, st>>>(d_data, n, to_montgomery ? 1 : 0);

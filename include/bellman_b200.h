@@ -130,6 +130,8 @@ int bb_point_add(int group, const void* a_affine, const void* b_affine, void* ou
 int bb_point_mul(int group, const void* a_affine, const void* fr_scalar, int form, void* out_affine);
 /* GroupEncoding::to_bytes: G1 48 B / G2 96 B compressed ZCash encoding */
 int bb_point_compress(int group, const void* affine, uint8_t* out);
+/* in-place canonical <-> Montgomery conversion of n Fp coordinates (host; parameter files) */
+int bb_fp_convert(void* fp_inout, size_t n, int to_montgomery);
 /* out[i] = [k_i] * generator, computed on the device (fixed-base); used to manufacture
  * synthetic CRS material of benchmark size (generator.rs:271-296,398-415 equivalent). */
 int bb_fixed_base_mul(bb_ctx* ctx, int group, const void* fr_scalars, size_t n, int form, void* out_affine);

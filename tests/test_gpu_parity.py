@@ -356,6 +356,10 @@ def test_prove_mimc322_matches_oracle(worker):
         assert len(proof) == 192                                     # groth16/src/lib.rs:559
         assert proof == mc.prove(r, s)
         assert proof == mc.expected_proof(r, s)
+    # a key that went through Parameters::write / Parameters::read (groth16/src/lib.rs:258-398)
+    from bellman_b200 import params_io
+    reloaded = bb.Parameters(worker, params_io.read_parameters(params_io.write_parameters(mc.export_params())))
+    assert bb.create_proof(asg, reloaded, r, s) == proof
     # "the proof verifies under the reference verifier": Proof::read + verify_proof
     # (groth16/src/lib.rs:47-99, verifier.rs:23-58) over the oracle's pairing
     from oracle.oracle0 import pairing as PR
