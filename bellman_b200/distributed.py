@@ -38,3 +38,37 @@ def max_over_ranks(seconds, group=None):
     t = torch.tensor([seconds], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+def create_proof_sharded(assignment, params, full_vk_params, r, s, device_ptrs=None, group=None):
+    """One proof over all ranks of `group` (create_proof, groth16/src/prover.rs:217-360, with the
+    MSMs sharded): every rank runs prove_partials on its shard, the 960-byte blobs AND each rank's
+    status are all-gathered in the same collective, and rank 0 finalises.  A SynthesisError on any
+    rank is re-raised on every rank (nobody is left waiting in the all-gather).  Returns the 192
+    proof bytes on rank 0, None elsewhere.  `full_vk_params` is any Parameters object of this rank
+    (only its verifying-key elements are read by finalize)."""
+    import torch
+    import torch.distributed as dist
+
+    from . import BackendError, SynthesisError, _ERRORS, finalize, prove_partials
+
+    status, blob, msg = 0, bytes(PARTIALS_BYTES), ""
+    try:
+        blob = prove_partials(assignment, params, device_ptrs)
+    except (SynthesisError, AssertionError, BackendError) as e:
+        msg = str(e)
+        status = next((code for code, cls in _ERRORS.items() if isinstance(e, cls)), 17)
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    mine = torch.frombuffer(bytearray(blob + bytes([status])), dtype=torch.uint8).to(device)
+    out = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(out, mine, group=group)
+    gathered = [bytes(t.cpu().numpy()) for t in out]
+    for rank, g in enumerate(gathered):
+        if g[PARTIALS_BYTES]:
+            code = g[PARTIALS_BYTES]
+            raise _ERRORS.get(code, BackendError)(f"rank {rank} failed with bb_status {code}" + (f": {msg}" if msg else ""))
+    if dist.get_rank(group) == 0:
+        return finalize(full_vk_params, [g[:PARTIALS_BYTES] for g in gathered], r, s)
+    return None

@@ -209,6 +209,7 @@ def run_prove(args):
     import torch.distributed as dist
 
     import bellman_b200 as bb
+    from bellman_b200.distributed import create_proof_sharded
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -248,18 +249,12 @@ def run_prove(args):
         keep.append(t)
         dev[name] = t.data_ptr()
     torch.cuda.synchronize()
-    gather_buf = torch.zeros(bb.PARTIALS_BYTES, dtype=torch.uint8, device=f"cuda:{local}")
-    gathered = [torch.zeros_like(gather_buf) for _ in range(world)]
 
     def step(device_ptrs):
         if world == 1:
             return bb.create_proof(asg, params, r, s, device_ptrs)
-        part = bb.prove_partials(asg, params, device_ptrs)
-        gather_buf.copy_(torch.frombuffer(bytearray(part), dtype=torch.uint8), non_blocking=False)
-        dist.all_gather(gathered, gather_buf)            # the one exchange step: per-shard partial sums
-        if rank == 0:
-            return bb.finalize(params, [bytes(g.cpu().numpy()) for g in gathered], r, s)
-        return None
+        # shards -> one all-gather of partial sums (+ statuses) -> finalize on rank 0
+        return create_proof_sharded(asg, params, params, r, s, device_ptrs)
 
     def sync():
         worker.synchronize()
@@ -338,6 +333,8 @@ def run_prove(args):
                      "launches": int(acc_launches), "avg_launch_ms": acc_ms / acc_launches if acc_launches else None,
                      "algorithmic_bytes_per_pair": 128,
                      "share_of_step": (acc_ms / max(world, 1)) / (1e3 * dt_val) if dt_val else None,
+                     "share_note": "sum of this kernel's launch durations (CUDA events on each job's stream) over the step time; "
+                                   "its launches overlap other streams' kernels, so the sum can approach or exceed the step",
                      "note": "integer-ALU bound, not HBM bound (SURVEY.md 8d): see integer_roofline",
                      "integer_roofline": {"bound": "int32 multiplier", "unit": "G Fp-mul/s",
                                           "achieved": (10.0 * 16 * acc_units / max(world, 1) / (acc_ms * 1e-3) / 1e9) if acc_ms > 0 else None,

@@ -30,6 +30,18 @@ def test_every_declared_symbol_is_exported():
         assert hasattr(lib, name), f"{name} declared in include/bellman_b200.h but not exported"
 
 
+def test_header_is_plain_c():
+    """the boundary is a C ABI: the header must compile as C99 (no C++ or torch types)"""
+    import subprocess, tempfile
+    src = "#include \"bellman_b200.h\"\nint main(void) { bb_witness w; bb_crs_desc d; (void)w; (void)d; return BB_PARTIALS_BYTES == 960 ? 0 : 1; }\n"
+    with tempfile.NamedTemporaryFile("w", suffix=".c", delete=False) as f:
+        f.write(src)
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                          "-fsyntax-only", f.name], capture_output=True, text=True)
+    os.unlink(f.name)
+    assert res.returncode == 0, res.stderr
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():

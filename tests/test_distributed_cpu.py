@@ -41,6 +41,18 @@ WORKER = textwrap.dedent('''
     assert max_over_ranks(float(rank)) == world - 1
     ranges = [shard_range(n, r, world) for r in range(world)]
     assert ranges[0][0] == 0 and ranges[-1][1] == n and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    # error on one rank: every rank raises, nobody hangs in the collective
+    import bellman_b200.distributed as D
+    def fake_partials(assignment, params, device_ptrs=None):
+        if rank == 1:
+            raise bb.UnexpectedIdentity("[bb_status 2] identity in the CRS shard of rank 1")
+        return bytes(bb.PARTIALS_BYTES)
+    bb.prove_partials = fake_partials
+    try:
+        D.create_proof_sharded(None, None, None, 1, 2)
+        raise SystemExit("expected UnexpectedIdentity")
+    except bb.UnexpectedIdentity as e:
+        assert "rank 1" in str(e)
     dist.destroy_process_group()
     print("rank", rank, "ok")
 ''')
