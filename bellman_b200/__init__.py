@@ -304,6 +304,38 @@ class EvaluationDomain:
         _check(load_library().bb_ntt(self.worker._h, _ptr(self.coeffs), C.c_uint32(self.exp), C.c_int(mode),
                                      C.c_int(FORM_MONTGOMERY)))
 
+    # Fr as Python integers <-> the Montgomery limbs of the buffers (host helpers of the mirror)
+    FR_MODULUS = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    MULTIPLICATIVE_GENERATOR = 7
+
+    @classmethod
+    def _to_mont(cls, v):
+        m = (v % cls.FR_MODULUS) * (1 << 256) % cls.FR_MODULUS
+        return np.array([(m >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)], dtype=np.uint64)
+
+    def _pointwise(self, op, other=None, k=None):
+        b = None if other is None else _c64(other, 4)
+        if b is not None:
+            assert b.shape == self.coeffs.shape                # assert_eq!(self.coeffs.len(), other.coeffs.len())
+        kk = None if k is None else self._to_mont(k)
+        _check(load_library().bb_domain_pointwise(self.worker._h, C.c_int(op), _ptr(self.coeffs), _ptr(b),
+                                                  C.c_size_t(self.coeffs.shape[0]), _ptr(kk)))
+
+    def mul_assign(self, other):                           # domain.rs:154-170
+        self._pointwise(0, other.coeffs if isinstance(other, EvaluationDomain) else other)
+
+    def sub_assign(self, other):                           # :173-189
+        self._pointwise(1, other.coeffs if isinstance(other, EvaluationDomain) else other)
+
+    def distribute_powers(self, g):                        # :101-113 (g: Python integer)
+        self._pointwise(3, k=g)
+
+    def z(self, tau):                                      # :129-134, tau^m - 1 as a Python integer
+        return (pow(tau, self.coeffs.shape[0], self.FR_MODULUS) - 1) % self.FR_MODULUS
+
+    def divide_by_z_on_coset(self):                        # :139-151
+        self._pointwise(2, k=pow(self.z(self.MULTIPLICATIVE_GENERATOR), -1, self.FR_MODULUS))
+
     def fft(self): self._run(NTT_FFT)                      # domain.rs:81-83
     def ifft(self): self._run(NTT_IFFT)                    # :85-99
     def coset_fft(self): self._run(NTT_COSET_FFT)          # :115-118

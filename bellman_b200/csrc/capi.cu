@@ -361,6 +361,25 @@ int bb_ntt(bb_ctx* ctx, void* fr_inout, uint32_t log_n, int mode, int form) {
     return BB_OK;
 }
 
+int bb_domain_pointwise(bb_ctx* ctx, int op, void* fr_a_inout, const void* fr_b, size_t n, const void* fr_k) {
+    if (!ctx || (n && !fr_a_inout) || op < 0 || op > 3) { set_error("bb_domain_pointwise: bad argument"); return BB_ERR_ARG; }
+    if (op <= 1 && n && !fr_b) { set_error("bb_domain_pointwise: op %d needs a second vector", op); return BB_ERR_ARG; }
+    if (op >= 2 && !fr_k) { set_error("bb_domain_pointwise: op %d needs a scalar", op); return BB_ERR_ARG; }
+    BB_CUDA(cudaSetDevice(ctx->device));
+    DevBuf d_a, d_b;
+    BB_TRY(d_a.alloc(ctx, n * 32));
+    BB_TRY(d_b.alloc(ctx, n * 32));
+    cudaStream_t st = ctx->main_stream;
+    BB_CUDA(cudaMemcpyAsync(d_a.p, fr_a_inout, n * 32, cudaMemcpyHostToDevice, st));
+    if (op <= 1) BB_CUDA(cudaMemcpyAsync(d_b.p, fr_b, n * 32, cudaMemcpyHostToDevice, st));
+    Fr k = Fr::zero();
+    if (fr_k) std::memcpy(k.l, fr_k, 32);
+    BB_TRY(domain_pointwise_device(ctx, st, d_a.as<Fr>(), d_b.as<Fr>(), n, op, k));
+    BB_CUDA(cudaMemcpyAsync(fr_a_inout, d_a.p, n * 32, cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    return BB_OK;
+}
+
 int bb_h_poly(bb_ctx* ctx, const void* a, const void* b, const void* c, size_t n, void* h_out, size_t* m_out) {
     if (!ctx || !h_out || (n && (!a || !b || !c))) { set_error("bb_h_poly: null argument"); return BB_ERR_ARG; }
     BB_CUDA(cudaSetDevice(ctx->device));

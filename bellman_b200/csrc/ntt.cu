@@ -70,6 +70,21 @@ __global__ void __launch_bounds__(256) k_fr_convert(Fr* data, size_t n, int to_m
     st_fr(data + i, to_mont ? fr_from_canonical(v) : fr_to_canonical(v));
 }
 
+// EvaluationDomain's O(n) methods as stand-alone operations (inside create_proof they are fused
+// into the transforms, see h_poly_device): op 0 mul_assign a*=b (domain.rs:154-170), 1 sub_assign
+// a-=b (:173-189), 2 scale a*=k (divide_by_z_on_coset :139-151, ifft's m^-1 :88-98),
+// 3 distribute_powers a[i]*=k^i (:101-113)
+__global__ void __launch_bounds__(256) k_domain_pointwise(Fr* a, const Fr* b, size_t n, int op, Fr k) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr x = ld_fr(a + i);
+    if (op == 0) x = x * ld_fr(b + i);
+    else if (op == 1) x = x - ld_fr(b + i);
+    else if (op == 2) x = x * k;
+    else x = x * k.pow_u64((uint64_t)i, fr_one());
+    st_fr(a + i, x);
+}
+
 struct PassArgs {
     const Fr* src;
     Fr* dst;
@@ -322,6 +337,14 @@ int h_poly_device(bb_ctx* ctx, cudaStream_t st, Fr* d_a, Fr* d_b, Fr* d_c, Fr* d
     Fusion fin;                         // mul_assign, sub_assign, divide_by_z_on_coset, icoset_fft (:232-237)
     fin.src_b = d_b; fin.src_c = d_c; fin.post = gz;
     return run_passes(ctx, st, d_a, d_a, d_tmp, log_m, tw_i, fin);
+}
+
+int domain_pointwise_device(bb_ctx* ctx, cudaStream_t st, Fr* d_a, const Fr* d_b, size_t n, int op, const Fr& k) {
+    if (!n) return BB_OK;
+    k_domain_pointwise<<<cdiv(n, 256), 256, 0, st>>>(d_a, d_b, n, op, k);
+    ctx->count_launch();
+    BB_CUDA(cudaGetLastError());
+    return BB_OK;
 }
 
 void ntt_free_tables(bb_ctx* ctx) {

@@ -88,6 +88,14 @@ int bb_ntt(bb_ctx* ctx, void* fr_inout, uint32_t log_n, int mode, int form);
 /* same, on a device buffer (Montgomery form) */
 int bb_ntt_device(bb_ctx* ctx, void* d_fr_inout, uint32_t log_n, int mode);
 
+/* EvaluationDomain's O(n) methods as stand-alone calls on host buffers (Montgomery Fr); inside
+ * bb_h_poly / bb_groth16_prove they are fused into the transforms instead.
+ *   op 0  mul_assign   a[i] *= b[i]          (src/domain.rs:154-170)
+ *   op 1  sub_assign   a[i] -= b[i]          (:173-189)
+ *   op 2  scale        a[i] *= k             (divide_by_z_on_coset with k = 1/z(g), :139-151)
+ *   op 3  distribute_powers  a[i] *= k^i     (:101-113) */
+int bb_domain_pointwise(bb_ctx* ctx, int op, void* fr_a_inout, const void* fr_b, size_t n, const void* fr_k);
+
 /* The H-polynomial block of create_proof (groth16/src/prover.rs:221-240): from_coeffs on
  * a,b,c (pads to m = 2^k >= n), 3x ifft, 3x coset_fft, mul_assign, sub_assign,
  * divide_by_z_on_coset, icoset_fft, truncate to m-1 coefficients.

@@ -182,6 +182,34 @@ def test_ntt_full_size_round_trips(worker):
         worker.device_free(d)
 
 
+def test_domain_methods_compose_like_the_reference(worker):
+    """The H block of create_proof written out with the individual EvaluationDomain methods
+    (prover.rs:222-240) equals the fused bb_h_poly and the oracle; distribute_powers + fft
+    equals coset_fft (domain.rs:115-118)."""
+    n = 700
+    a, b = o1.fr_random(501, n), o1.fr_random(502, n)
+    c = o1.fr_mul(a, b)
+    doms = [bb.EvaluationDomain.from_coeffs(worker, v) for v in (a, b, c)]
+    for d in doms:
+        d.ifft()
+        d.coset_fft()
+    A, B, Cc = doms
+    A.mul_assign(B)
+    A.sub_assign(Cc)
+    A.divide_by_z_on_coset()
+    A.icoset_fft()
+    want = o1.h_poly(a, b, c)
+    assert np.array_equal(A.into_coeffs()[:-1], want)
+    assert np.array_equal(o1.fr_to_canonical(want), bb.h_poly(worker, a, b, c))
+    v = o1.fr_random(503, 1 << 9)
+    d1 = bb.EvaluationDomain.from_coeffs(worker, v)
+    d1.distribute_powers(7)
+    d1.fft()
+    assert np.array_equal(d1.into_coeffs(), o1.fft(v, o1.COSET_FFT))
+    tau = 0x123456789abcdef
+    assert d1.z(tau) == (pow(tau, 512, R) - 1) % R
+
+
 def test_h_poly_matches_oracle(worker):
     for n in (1, 2, 5, 646, 5000):
         a, b = o1.fr_random(200 + n, n), o1.fr_random(300 + n, n)
