@@ -422,6 +422,7 @@ class Parameters:
         h = C.c_void_p()
         _check(load_library().bb_crs_create(worker._h, C.byref(d), C.byref(h)))
         self._h = h
+        self._keep = None                    # the vectors are resident in HBM now
         worker._children.add(self)
 
     @classmethod

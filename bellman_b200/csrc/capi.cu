@@ -82,8 +82,9 @@ template <class F>
 struct FixedTable {
     Affine<F>* d_table = nullptr;
 };
-FixedTable<Fp> g_tab1;
-FixedTable<Fp2> g_tab2;
+constexpr int MAX_DEVICES = 64;
+FixedTable<Fp> g_tab1[MAX_DEVICES];      // one table per device (a process may open several contexts)
+FixedTable<Fp2> g_tab2[MAX_DEVICES];
 std::mutex g_tab_mu;
 
 template <class F>
@@ -207,8 +208,9 @@ int selftest_run(bb_ctx* ctx, K kernel, const void* a, const void* b, void* o, s
 
 namespace bb {
 int fixed_base_mul_device(bb_ctx* ctx, int group, const Fr* d_scalars, size_t n, bool montgomery, void* d_out, cudaStream_t st) {
-    if (group == BB_G1) return fixed_base_mul_dev<Fp>(ctx, g_tab1, g1_generator(), d_scalars, n, montgomery, (G1Affine*)d_out, st);
-    return fixed_base_mul_dev<Fp2>(ctx, g_tab2, g2_generator(), d_scalars, n, montgomery, (G2Affine*)d_out, st);
+    if (ctx->device < 0 || ctx->device >= MAX_DEVICES) { set_error("device ordinal out of range"); return BB_ERR_ARG; }
+    if (group == BB_G1) return fixed_base_mul_dev<Fp>(ctx, g_tab1[ctx->device], g1_generator(), d_scalars, n, montgomery, (G1Affine*)d_out, st);
+    return fixed_base_mul_dev<Fp2>(ctx, g_tab2[ctx->device], g2_generator(), d_scalars, n, montgomery, (G2Affine*)d_out, st);
 }
 }  // namespace bb
 
@@ -489,8 +491,9 @@ int bb_fp_convert(void* fp_inout, size_t n, int to_montgomery) {
 int bb_fixed_base_mul(bb_ctx* ctx, int group, const void* scalars, size_t n, int form, void* out) {
     if (!ctx || (n && (!scalars || !out))) { set_error("bb_fixed_base_mul: null argument"); return BB_ERR_ARG; }
     BB_CUDA(cudaSetDevice(ctx->device));
-    if (group == BB_G1) return fixed_base_mul<Fp>(ctx, g_tab1, g1_generator(), scalars, n, form, out);
-    if (group == BB_G2) return fixed_base_mul<Fp2>(ctx, g_tab2, g2_generator(), scalars, n, form, out);
+    if (ctx->device < 0 || ctx->device >= MAX_DEVICES) { set_error("device ordinal out of range"); return BB_ERR_ARG; }
+    if (group == BB_G1) return fixed_base_mul<Fp>(ctx, g_tab1[ctx->device], g1_generator(), scalars, n, form, out);
+    if (group == BB_G2) return fixed_base_mul<Fp2>(ctx, g_tab2[ctx->device], g2_generator(), scalars, n, form, out);
     set_error("bad group");
     return BB_ERR_ARG;
 }

@@ -156,17 +156,6 @@ __global__ void __launch_bounds__(256) k_ntt_pass(PassArgs A) {
 
 static Fr h_pow(const Fr& b, uint64_t e) { return b.pow_u64(e, fr_one()); }
 
-static int make_powers(bb_ctx* ctx, cudaStream_t st, Fr** out, size_t n, const Fr& base, const Fr& scale) {
-    void* p = nullptr;
-    BB_TRY(ctx->alloc(n * sizeof(Fr), &p));
-    *out = (Fr*)p;
-    size_t threads = (n + 31) / 32;
-    k_powers<<<cdiv(threads, 256), 256, 0, st>>>(*out, n, base, scale);
-    ctx->count_launch();
-    BB_CUDA(cudaGetLastError());
-    return BB_OK;
-}
-
 struct DomainConsts { Fr omega, omegainv, g, ginv, minv, zinv; };
 
 static DomainConsts domain_consts(uint32_t log_n) {

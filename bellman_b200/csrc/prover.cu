@@ -26,9 +26,6 @@ void shard_policy(const bb_ctx* ctx, uint32_t idx, uint32_t cnt, uint32_t* b, ui
     *nv = w; *nb = cnt / w; *v = idx % w; *b = idx / w;
 }
 
-template <class F>
-bool affine_equal(const Affine<F>& a, const Affine<F>& b) { return a.x == b.x && a.y == b.y; }
-
 // scalar multiplication on the host (the five Affine * Fr of prover.rs:326-337 and the two
 // MulAssign<Fr> of :342,351); k is a canonical little-endian 256-bit integer
 template <class F>

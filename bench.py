@@ -15,7 +15,6 @@ The oracle (oracle/) is used only by the cpu_baseline leg and by --impl referenc
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
@@ -184,26 +183,6 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU legs
 # ------------------------------------------------------------------------------------------------
-def random_scalars(rng, n):
-    """pseudorandom canonical scalars < 2^254 < r (dlogs of the synthetic CRS)"""
-    k = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
-    k[:, 3] &= np.uint64((1 << 62) - 1)
-    return k
-
-
-def make_crs(bb, worker, shape, seed):
-    """Parameters-shaped base vectors [k_i]G with pseudorandom k_i, produced on the device.
-    Same lengths as generate_parameters' output for this circuit (generator.rs:247,303-307,
-    491-505).  Not a trapdoor CRS: valid-CRS parity at this size is
-    tests/test_gpu_parity.py::test_prove_synthetic_chain_trapdoor."""
-    rng = np.random.default_rng(seed)
-    n_a = shape["num_inputs"] + shape["a_aux_total"]
-    n_b = shape["b_in_total"] + shape["b_aux_total"]
-    mk = lambda g, n: bb.fixed_base_mul(worker, g, random_scalars(rng, n), bb.FORM_CANONICAL)
-    return dict(vk_g1=mk(bb.G1, 3), vk_g2=mk(bb.G2, 3), h=mk(bb.G1, shape["m"] - 1), l=mk(bb.G1, shape["num_aux"]),
-                a=mk(bb.G1, n_a), b_g1=mk(bb.G1, n_b), b_g2=mk(bb.G2, n_b))
-
-
 def run_prove(args):
     import torch
     import torch.distributed as dist
