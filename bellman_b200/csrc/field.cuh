@@ -10,8 +10,11 @@ namespace bb {
 
 // per-translation-unit copies of the moduli in constant memory: operands of the
 // reduction rows come straight from the constant bank, no registers.
+#if defined(__CUDACC__)
 static __device__ __constant__ uint32_t kFrMod[8] = {BBC_FR_MOD_LIST};
 static __device__ __constant__ uint32_t kFpMod[12] = {BBC_FP_MOD_LIST};
+static __device__ __constant__ uint32_t kFpModSq[24] = {BBC_FP_MODSQ_LIST};   // p^2
+#endif
 
 struct FrCfg {
     static constexpr int N = 8;
@@ -19,6 +22,8 @@ struct FrCfg {
     static constexpr uint64_t INV64 = 0xfffffffeffffffffull;
 #if defined(__CUDACC__)
     static __device__ __forceinline__ uint32_t dmod(int k) { return kFrMod[k]; }
+#elif defined(BB_EMULATE_PTX)
+    static uint32_t dmod(int k) { return bbc::FR_MOD[k]; }
 #endif
     static const uint32_t* hmod() { return bbc::FR_MOD; }
 };
@@ -28,6 +33,8 @@ struct FpCfg {
     static constexpr uint64_t INV64 = 0x89f3fffcfffcfffdull;
 #if defined(__CUDACC__)
     static __device__ __forceinline__ uint32_t dmod(int k) { return kFpMod[k]; }
+#elif defined(BB_EMULATE_PTX)
+    static uint32_t dmod(int k) { return bbc::FP_MOD[k]; }
 #endif
     static const uint32_t* hmod() { return bbc::FP_MOD; }
 };
@@ -72,6 +79,11 @@ BB_HD Fp fp_inv(const Fp& a) {
 // Fp2 = Fp[u]/(u^2+1)
 struct Fp2 {
     Fp c0, c1;
+#if defined(__CUDACC__)
+    static __device__ __forceinline__ uint32_t modsq(int k) { return kFpModSq[k]; }
+#elif defined(BB_EMULATE_PTX)
+    static uint32_t modsq(int k) { return bbc::FP_MODSQ[k]; }
+#endif
     BB_HD static Fp2 zero() { return {Fp::zero(), Fp::zero()}; }
     BB_HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
     BB_HD bool operator==(const Fp2& o) const { return c0 == o.c0 && c1 == o.c1; }
@@ -79,9 +91,43 @@ struct Fp2 {
     BB_HD Fp2 operator+(const Fp2& o) const { return {c0 + o.c0, c1 + o.c1}; }
     BB_HD Fp2 operator-(const Fp2& o) const { return {c0 - o.c0, c1 - o.c1}; }
     BB_HD_NOINLINE Fp2 operator*(const Fp2& o) const { // Karatsuba: 3 Fp products
+#if defined(BB_DEVPATH)
+        // lazy reduction: three 24-limb integer products, two Montgomery reductions.
+        //   c0 = redc(a0 b0 + p^2 - a1 b1)              (< 2 p^2)
+        //   c1 = redc((a0+a1)(b0+b1) - a0 b0 - a1 b1)   (= a0 b1 + a1 b0 < 2 p^2; sums < 2p fit 12 limbs)
+        uint32_t T0[24], T1[24];
+        wide_mul<12>(T0, c0.l, o.c0.l);
+        wide_mul<12>(T1, c1.l, o.c1.l);
+        uint32_t D[24];
+        D[0] = ptx::add_cc(T0[0], modsq(0));
+#pragma unroll
+        for (int k = 1; k < 24; k++) D[k] = ptx::addc_cc(T0[k], modsq(k));
+        D[0] = ptx::sub_cc(D[0], T1[0]);
+#pragma unroll
+        for (int k = 1; k < 24; k++) D[k] = ptx::subc_cc(D[k], T1[k]);
+        T0[0] = ptx::add_cc(T0[0], T1[0]);                 // S = a0 b0 + a1 b1
+#pragma unroll
+        for (int k = 1; k < 24; k++) T0[k] = ptx::addc_cc(T0[k], T1[k]);
+        Fp2 r;
+        redc_wide<FpCfg>(r.c0.l, D);
+        uint32_t sa[12], sb[12];
+        sa[0] = ptx::add_cc(c0.l[0], c1.l[0]);
+#pragma unroll
+        for (int k = 1; k < 12; k++) sa[k] = ptx::addc_cc(c0.l[k], c1.l[k]);
+        sb[0] = ptx::add_cc(o.c0.l[0], o.c1.l[0]);
+#pragma unroll
+        for (int k = 1; k < 12; k++) sb[k] = ptx::addc_cc(o.c0.l[k], o.c1.l[k]);
+        wide_mul<12>(T1, sa, sb);
+        T1[0] = ptx::sub_cc(T1[0], T0[0]);
+#pragma unroll
+        for (int k = 1; k < 24; k++) T1[k] = ptx::subc_cc(T1[k], T0[k]);
+        redc_wide<FpCfg>(r.c1.l, T1);
+        return r;
+#else
         Fp aa = c0 * o.c0, bb_ = c1 * o.c1;
         Fp t = (c0 + c1) * (o.c0 + o.c1);
         return {aa - bb_, t - aa - bb_};
+#endif
     }
     BB_HD_NOINLINE Fp2 sqr() const {                   // (c0+c1)(c0-c1), 2 c0 c1
         Fp s = c0 + c1, d = c0 - c1, m = c0 * c1;

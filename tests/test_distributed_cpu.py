@@ -54,7 +54,7 @@ WORKER = textwrap.dedent('''
     except bb.UnexpectedIdentity as e:
         assert "rank 1" in str(e)
     dist.destroy_process_group()
-    print("rank", rank, "ok")
+    open(os.path.join(os.path.dirname(os.path.abspath(__file__)), f"ok.{rank}"), "w").write("ok")   # one file per rank: stdout of the two ranks can interleave
 ''')
 
 
@@ -66,4 +66,4 @@ def test_sharded_partials_gloo_world2(tmp_path):
            "--master-port", "29517", str(script)]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
-    assert "rank 0 ok" in res.stdout and "rank 1 ok" in res.stdout
+    assert (tmp_path / "ok.0").exists() and (tmp_path / "ok.1").exists(), res.stdout + res.stderr
