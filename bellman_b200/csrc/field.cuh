@@ -91,7 +91,7 @@ struct Fp2 {
     BB_HD Fp2 operator+(const Fp2& o) const { return {c0 + o.c0, c1 + o.c1}; }
     BB_HD Fp2 operator-(const Fp2& o) const { return {c0 - o.c0, c1 - o.c1}; }
     BB_HD_NOINLINE Fp2 operator*(const Fp2& o) const { // Karatsuba: 3 Fp products
-#if defined(BB_DEVPATH)
+#if defined(BB_DEVPATH) && BB_FP2_LAZY
         // lazy reduction: three 24-limb integer products, two Montgomery reductions.
         //   c0 = redc(a0 b0 + p^2 - a1 b1)              (< 2 p^2)
         //   c1 = redc((a0+a1)(b0+b1) - a0 b0 - a1 b1)   (= a0 b1 + a1 b0 < 2 p^2; sums < 2p fit 12 limbs)

@@ -33,6 +33,23 @@
 #define BB_HD_NOINLINE inline
 #endif
 
+// Compile-time arithmetic variants.  Results are bit-identical in all of them; each is executed on
+// the CPU by tests/test_emulated_device_field.py and was run through the GPU parity suite on B200.
+//   BB_FP_WIDE_SQR  dedicated 12-limb squaring (wide_sqr + redc_wide) instead of a*a:  -29 % multiplier
+//                   instructions per squaring.
+//   BB_FP2_LAZY     lazily reduced Fp2 product (3 wide products, 2 reductions): -13 % multiplier
+//                   instructions, +9 % instructions overall.
+// Both were measured SLOWER on B200 in the 2^20 prove (50.7 / 50.5 ms against 48.9 ms, same box, round 1):
+// the bucket kernels run 4-8 warps per SM and are bound by the latency of the serial carry chains,
+// which both variants lengthen (24-limb add/shift/diagonal chains), not by multiplier issue slots.
+// They stay off; with both at 0 the generated SASS is identical to the plain merged product.
+#ifndef BB_FP_WIDE_SQR
+#define BB_FP_WIDE_SQR 0
+#endif
+#ifndef BB_FP2_LAZY
+#define BB_FP2_LAZY 0
+#endif
+
 namespace bb {
 
 // BB_EMULATE_PTX (host compilers only, tests/native/): the carry-chain primitives below are
@@ -407,7 +424,7 @@ struct alignas(16) Fe {
     // device: dedicated squaring (wide_sqr + redc_wide) for the 12-limb field, where it saves a
     // quarter of the multiplier work; the 8-limb field keeps the merged product
     BB_HD Fe sqr() const {
-#if defined(BB_DEVPATH)
+#if defined(BB_DEVPATH) && BB_FP_WIDE_SQR
         if (N >= 12) {
             uint32_t T[2 * N];
             wide_sqr<N>(T, l);

@@ -20,10 +20,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 R_MOD, P_MOD = F.FR_MODULUS, F.FP_MODULUS
 
 
-@pytest.fixture(scope="module")
-def emu(tmp_path_factory):
-    out = tmp_path_factory.mktemp("emu") / "libemu_field.so"
-    subprocess.run(["g++", "-O1", "-std=c++17", "-DBB_EMULATE_PTX", "-I", os.path.join(ROOT, "bellman_b200/csrc"),
+# (BB_FP_WIDE_SQR, BB_FP2_LAZY): the shipped default (0, 0) and the alternative arithmetic variants
+@pytest.fixture(scope="module", params=[(0, 0), (1, 0), (1, 1)], ids=["default", "wide-sqr", "wide-sqr+lazy-fp2"])
+def emu(request, tmp_path_factory):
+    sqr, lazy = request.param
+    out = tmp_path_factory.mktemp("emu") / f"libemu_field_{sqr}{lazy}.so"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-DBB_EMULATE_PTX", f"-DBB_FP_WIDE_SQR={sqr}", f"-DBB_FP2_LAZY={lazy}",
+                    "-I", os.path.join(ROOT, "bellman_b200/csrc"),
                     "-shared", "-fPIC", os.path.join(ROOT, "tests/native/emu_field.cpp"), "-o", str(out)], check=True)
     return ctypes.CDLL(str(out))
 
