@@ -1,0 +1,147 @@
+"""The product's own sources -- host orchestration and every kernel of the MSM / NTT / prover
+pipeline -- executed on host threads (tests/native/cuda_emu/cuda_runtime.h, built by
+tests/native/build_emu.py from the unmodified bellman_b200/csrc/*.cu) and compared with the CPU
+oracle at small sizes.
+
+What this covers without a GPU: the launch sequences, buffer sizes, index arithmetic, counting
+sort, bucket scheduling, task splitting, multi-level bucket reduction, NTT tiling, the prover's job
+graph, shard policy and error semantics -- through the same C ABI and the same Python mirror the
+GPU tests use (the test bodies are the ones in test_gpu_parity.py wherever their sizes allow).
+What it does not cover: anything nvcc/ptxas/the hardware does.  The emulated library is test
+infrastructure: it is built into a temporary directory and never loaded by the product.
+"""
+import importlib.util
+import os
+import random
+
+import numpy as np
+import pytest
+
+import bellman_b200 as bb
+from oracle import o1
+
+import test_gpu_parity as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+R = o1.FR_MODULUS
+
+
+def _load_builder():
+    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tests", "native", "build_emu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture(scope="module")
+def worker(tmp_path_factory):
+    lib, launches = _load_builder().build(str(tmp_path_factory.mktemp("bb_emu")))
+    assert launches >= 30
+    saved = (bb.LIB_PATH, bb._lib)
+    bb.LIB_PATH, bb._lib = lib, None                 # this module only: the mirror talks to the emulated library
+    try:
+        w = bb.Worker(0)
+        yield w
+        w.close()
+    finally:
+        bb.LIB_PATH, bb._lib = saved
+
+
+def test_emulated_field_and_point_kernels(worker):
+    G.test_field_arithmetic(worker)
+    G.test_point_arithmetic(worker)
+    G.test_bucket_reduction_kernels(worker)
+
+
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 5, 8, 9, 11, 12, 13])
+def test_emulated_ntt(worker, log_n):
+    G.test_ntt_matches_oracle(worker, log_n)
+
+
+def test_emulated_ntt_variants(worker):
+    G.test_ntt_tile_shapes_do_not_change_results(worker)
+    G.test_ntt_padding_and_degree_limit(worker)
+    G.test_ntt_canonical_form_is_also_exact(worker)
+    G.test_domain_methods_compose_like_the_reference(worker)
+    G.test_h_poly_matches_oracle(worker)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 32, 33, 1000])
+def test_emulated_multiexp_g1(worker, n):
+    G.test_multiexp_g1_matches_oracle(worker, n)
+
+
+@pytest.mark.parametrize("n", [0, 3, 40, 300])
+def test_emulated_multiexp_g2(worker, n):
+    G.test_multiexp_g2_matches_oracle(worker, n)
+
+
+def test_emulated_multiexp_windows(worker):
+    n = 700
+    bases = o1.g1_fixed_mul(o1.fr_random(41, n))
+    ex = o1.fr_random(42, n)
+    rc, want = o1.multiexp(1, bases, 0, None, ex)
+    try:
+        for c in (2, 3, 5, 8, 13, 15, 16):
+            worker.set_option("msm_window_bits", c)
+            assert np.array_equal(G._gpu_multiexp(worker, bb.G1, bases, 0, None, ex), want), c
+    finally:
+        worker.set_option("msm_window_bits", 0)
+
+
+def test_emulated_multiexp_density_fast_paths_and_skew(worker):
+    rng = np.random.default_rng(5)
+    n = 1200
+    dens = rng.random(n) < 0.5
+    k, off = int(dens.sum()), 7
+    bases = o1.g1_fixed_mul(o1.fr_random(51, off + k + 3))
+    ex = o1.fr_random(52, n)
+    kind = rng.integers(0, 4, n)
+    ex[kind == 0] = 0                                   # Exponent::Zero / One fast paths
+    ex[kind == 1] = o1.fr_from_ints([1])[0]
+    rc, want = o1.multiexp(1, bases, off, dens.astype(np.uint8), ex)
+    assert rc == 0
+    assert np.array_equal(G._gpu_multiexp(worker, bb.G1, bases, off, dens, ex), want)
+    # skewed scalars: the oversized-bucket (task) path
+    m = 1500
+    b2 = o1.g1_fixed_mul(o1.fr_random(81, m))
+    cases = {
+        "all twos": o1.fr_from_ints([2] * m),
+        "bytes+big": o1.fr_from_ints([int(x) for x in rng.integers(0, 256, m - 5)] + [R - 1, R - 2, 3, 1 << 200, 7]),
+        "same value": np.repeat(o1.fr_random(82, 1), m, axis=0),
+    }
+    for name, e in cases.items():
+        rc, want = o1.multiexp(1, b2, 0, None, e)
+        assert rc == 0 and np.array_equal(G._gpu_multiexp(worker, bb.G1, b2, 0, None, e), want), name
+    try:                                                # every bucket above 3 entries is cut into tasks
+        worker.set_option("msm_big_cap", 3)
+        e = o1.fr_random(83, m)
+        rc, want = o1.multiexp(1, b2, 0, None, e)
+        assert np.array_equal(G._gpu_multiexp(worker, bb.G1, b2, 0, None, e), want)
+    finally:
+        worker.set_option("msm_big_cap", 0)
+
+
+def test_emulated_multiexp_error_semantics(worker):
+    G.test_multiexp_error_semantics(worker)
+
+
+def test_emulated_prove_mimc322_and_shards(worker):
+    """BASELINE.json configs[0] through the whole prover, plus the (base range x window) shards"""
+    rng = random.Random(71)
+    mc = o1.Mimc(322, seed=3)
+    mc.set_toxic([rng.randrange(1, R) for _ in range(5)])
+    mc.generate()
+    params = bb.Parameters(worker, mc.export_params())
+    asg = G._assignment(mc.witness())
+    r, s = rng.randrange(R), rng.randrange(R)
+    proof = bb.create_proof(asg, params, r, s)
+    assert len(proof) == 192 and proof == mc.prove(r, s) == mc.expected_proof(r, s)
+    for count in (2, 8):                                 # 2 window shards; 2 base ranges x 4 window shards
+        parts = []
+        for k in range(count):
+            pk = bb.Parameters(worker, mc.export_params(), shard_index=k, shard_count=count)
+            parts.append(bb.prove_partials(asg, pk))
+            pk.free()
+        assert bb.finalize(params, parts, r, s) == proof, count
+
