@@ -102,7 +102,7 @@ def build(out_dir, extra_flags=()):
         subprocess.run(cmd, check=True)
         objs.append(obj)
     lib = os.path.join(out_dir, "libbellman_b200_emu.so")
-    subprocess.run(["g++", "-shared", "-pthread", "-o", lib, *objs], check=True)
+    subprocess.run(["g++", "-shared", "-pthread", *extra_flags, "-o", lib, *objs], check=True)
     return lib, launches
 
 

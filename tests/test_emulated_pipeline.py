@@ -35,8 +35,10 @@ def _load_builder():
 
 @pytest.fixture(scope="module")
 def worker(tmp_path_factory):
-    lib, launches = _load_builder().build(str(tmp_path_factory.mktemp("bb_emu")))
-    assert launches >= 25
+    lib = os.environ.get("BB_EMU_LIB")               # a pre-built (e.g. sanitizer) variant, see tests/native/README.md
+    if not lib:
+        lib, launches = _load_builder().build(str(tmp_path_factory.mktemp("bb_emu")))
+        assert launches >= 25
     saved = (bb.LIB_PATH, bb._lib)
     bb.LIB_PATH, bb._lib = lib, None                 # this module only: the mirror talks to the emulated library
     try:
