@@ -1,6 +1,8 @@
 // bellman_b200: the device side of groth16::create_proof after synthesis
 // (/root/reference/groth16/src/prover.rs:217-360): CRS residency, the H pipeline, the eight
 // multiexps in flight, and the host finalisation.
+#include <functional>
+
 #include "bb_internal.cuh"
 
 using namespace bb;
@@ -154,7 +156,36 @@ void bb_crs_destroy(bb_crs* crs) {
     delete crs;
 }
 
-int bb_groth16_prove_partials(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, uint8_t* partials) {
+}  // extern "C"
+
+namespace {
+
+// x_i / zz_i, y_i / zzz_i for a handful of points with ONE field inversion (Montgomery's trick)
+template <class F>
+void batch_to_affine(const XYZZ<F>* in, int n, Affine<F>* out) {
+    F pre[8];
+    F acc = FieldOps<F>::one();
+    for (int i = 0; i < n; i++) { pre[i] = acc; if (!in[i].is_identity()) acc = acc * in[i].ZZZ; }
+    F inv = FieldOps<F>::inv(acc);
+    for (int i = n - 1; i >= 0; i--) {
+        if (in[i].is_identity()) { out[i] = Affine<F>::identity(); continue; }
+        F zi3 = inv * pre[i];
+        inv = inv * in[i].ZZZ;
+        F zi2 = (zi3 * in[i].ZZ).sqr();
+        out[i] = {in[i].X * zi2, in[i].Y * zi3};
+    }
+}
+
+bool delta_is_identity(const bb_crs* crs) {                                       // prover.rs:320-324
+    if (!crs->delta_g1.is_identity() && !crs->delta_g2.is_identity()) return false;
+    set_error("delta is the identity: subversion-CRS attack");
+    return true;
+}
+
+// The eight MSMs and the H pipeline of create_proof (prover.rs:221-318).  `while_device_runs`, if
+// given, is called once everything is queued and before the first wait: host work that needs no
+// MSM result goes there and overlaps the device.
+int prove_partials_impl(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, uint8_t* partials, const std::function<void()>* while_device_runs) {
     if (!ctx || !crs || !w || !partials) { set_error("bb_groth16_prove_partials: null argument"); return BB_ERR_ARG; }
     BB_CUDA(cudaSetDevice(ctx->device));
     const size_t n = w->n_constraints;
@@ -212,20 +243,48 @@ int bb_groth16_prove_partials(bb_ctx* ctx, const bb_crs* crs, const bb_witness* 
             start(0, crs->h, 0, nullptr, 0, d_a.p, m - 1, ev_h);                                            // :238-244
         }
     }
-    // wait() x8 (prover.rs:339-354); always drain every started job
-    size_t off = 0;
-    for (int k = 0; k < 8; k++) {
-        bool g2 = k >= 6;
-        if (jobs[k]) {
-            MsmResult r;
-            int sk = msm_wait_result(jobs[k], &r);
-            if (s == BB_OK && sk != BB_OK) s = sk;
-            if (sk == BB_OK) {
-                if (g2) { G2Affine a = r.x2.to_affine(); std::memcpy(partials + off, &a, 192); }
-                else { G1Affine a = r.g1.to_affine(); std::memcpy(partials + off, &a, 96); }
-            }
+    if (while_device_runs && *while_device_runs) (*while_device_runs)();
+    // wait() x8 (prover.rs:339-354); always drain every started job.  The h MSM was queued last
+    // (it follows the H pipeline), so it is waited for last: the host-side window folds of the
+    // other seven overlap it.
+    G1X sums1[6];
+    G2X sums2[2];
+    for (auto& p1 : sums1) p1 = G1X::identity();
+    for (auto& p2 : sums2) p2 = G2X::identity();
+    static const int wait_order[8] = {1, 2, 3, 4, 5, 6, 7, 0};
+    int slot_status[8] = {BB_OK, BB_OK, BB_OK, BB_OK, BB_OK, BB_OK, BB_OK, BB_OK};
+    for (int idx = 0; idx < 8; idx++) {
+        const int k = wait_order[idx];
+        if (!jobs[k]) continue;
+        MsmResult r;
+        slot_status[k] = msm_wait_result(jobs[k], &r);
+        if (slot_status[k] == BB_OK) {
+            if (k >= 6) sums2[k - 6] = r.x2;
+            else sums1[k] = r.g1;
         }
-        off += g2 ? 192 : 96;
+    }
+    if (s == BB_OK) {
+        // Which error create_proof reports when several apply: the density assert fires inside the
+        // multiexp() call itself (multiexp.rs:324-329; calls are made in slot order), the delta
+        // check comes before the first wait (prover.rs:320-324), and the waits run a_inputs, a_aux,
+        // b_g1_inputs, b_g1_aux, b_g2_inputs, b_g2_aux, h, l (:339-354).
+        static const int ref_wait_order[8] = {2, 3, 4, 5, 6, 7, 0, 1};
+        for (int k = 0; k < 8 && s == BB_OK; k++) if (slot_status[k] == BB_ERR_DENSITY_MISMATCH) s = slot_status[k];
+        if (s == BB_OK && delta_is_identity(crs)) s = BB_ERR_UNEXPECTED_IDENTITY;
+        for (int idx = 0; idx < 8 && s == BB_OK; idx++) s = slot_status[ref_wait_order[idx]];
+        // the message of the error that is reported (another job may have failed later)
+        if (s == BB_ERR_IO_UNEXPECTED_EOF) set_error("expected more bases from source");
+        else if (s == BB_ERR_UNEXPECTED_IDENTITY && !crs->delta_g1.is_identity() && !crs->delta_g2.is_identity())
+            set_error("encountered an identity element in the CRS");
+        else if (s == BB_ERR_DENSITY_MISMATCH) set_error("density map length differs from the number of exponents");
+    }
+    if (s == BB_OK) {
+        G1Affine a1[6];
+        G2Affine a2[2];
+        batch_to_affine<Fp>(sums1, 6, a1);
+        batch_to_affine<Fp2>(sums2, 2, a2);
+        std::memcpy(partials, a1, 6 * 96);
+        std::memcpy(partials + 576, a2, 2 * 192);
     }
     cudaStreamSynchronize(st);
     cudaStreamSynchronize(up);
@@ -234,13 +293,22 @@ int bb_groth16_prove_partials(bb_ctx* ctx, const bb_crs* crs, const bb_witness* 
     return s;
 }
 
-int bb_groth16_finalize(const bb_crs* crs, const uint8_t* partials, size_t count, const uint8_t* r_bytes, const uint8_t* s_bytes,
-                        uint8_t* proof) {
-    if (!crs || !partials || !count || !r_bytes || !s_bytes || !proof) { set_error("bb_groth16_finalize: null argument"); return BB_ERR_ARG; }
-    if (crs->delta_g1.is_identity() || crs->delta_g2.is_identity()) {              // prover.rs:320-324
-        set_error("delta is the identity: subversion-CRS attack");
-        return BB_ERR_UNEXPECTED_IDENTITY;
-    }
+// The terms of A, B, C that depend only on the key and on (r, s) -- prover.rs:326-337:
+//   g_a = delta_g1 r + alpha_g1,  g_b = delta_g2 s + beta_g2,  g_c = delta_g1 rs + alpha_g1 s + beta_g1 r
+struct ProofStatic { G1X g_a, g_c; G2X g_b; };
+
+void finalize_static(const bb_crs* crs, const Fr& r, const Fr& s, ProofStatic* out) {
+    Fr rs = fr_to_canonical(fr_from_canonical(r) * fr_from_canonical(s));        // rs.mul_assign(&s), :332-333
+    out->g_a = g1_host_mul(G1X::from_affine(crs->delta_g1), r.l);                 // :326-327
+    out->g_a.add_mixed(crs->alpha_g1);
+    out->g_b = g2_host_mul(G2X::from_affine(crs->delta_g2), s.l);                 // :328-329
+    out->g_b.add_mixed(crs->beta_g2);
+    out->g_c = g1_host_mul(G1X::from_affine(crs->delta_g1), rs.l);                // :335-337
+    out->g_c.add(g1_host_mul(G1X::from_affine(crs->alpha_g1), s.l));
+    out->g_c.add(g1_host_mul(G1X::from_affine(crs->beta_g1), r.l));
+}
+
+int finalize_impl(const bb_crs* crs, const uint8_t* partials, size_t count, const Fr& r, const Fr& s, const ProofStatic& stat, uint8_t* proof) {
     G1X sum1[6];
     G2X sum2[2];
     for (auto& p : sum1) p = G1X::identity();
@@ -250,17 +318,8 @@ int bb_groth16_finalize(const bb_crs* crs, const uint8_t* partials, size_t count
         for (int k = 0; k < 6; k++) { G1Affine a; std::memcpy(&a, base + 96 * k, 96); sum1[k].add_mixed(a); }
         for (int k = 0; k < 2; k++) { G2Affine a; std::memcpy(&a, base + 576 + 192 * k, 192); sum2[k].add_mixed(a); }
     }
-    Fr r, s;
-    std::memcpy(r.l, r_bytes, 32);
-    std::memcpy(s.l, s_bytes, 32);
-    Fr rs = fr_to_canonical(fr_from_canonical(r) * fr_from_canonical(s));        // rs.mul_assign(&s), :332-333
-    G1X g_a = g1_host_mul(G1X::from_affine(crs->delta_g1), r.l);                  // :326-327
-    g_a.add_mixed(crs->alpha_g1);
-    G2X g_b = g2_host_mul(G2X::from_affine(crs->delta_g2), s.l);                  // :328-329
-    g_b.add_mixed(crs->beta_g2);
-    G1X g_c = g1_host_mul(G1X::from_affine(crs->delta_g1), rs.l);                 // :335-337
-    g_c.add(g1_host_mul(G1X::from_affine(crs->alpha_g1), s.l));
-    g_c.add(g1_host_mul(G1X::from_affine(crs->beta_g1), r.l));
+    G1X g_a = stat.g_a, g_c = stat.g_c;
+    G2X g_b = stat.g_b;
     G1X a_answer = sum1[2];                                                       // :339-343
     a_answer.add(sum1[3]);
     g_a.add(a_answer);
@@ -273,18 +332,49 @@ int bb_groth16_finalize(const bb_crs* crs, const uint8_t* partials, size_t count
     g_c.add(g1_host_mul(b1_answer, r.l));
     g_c.add(sum1[0]);
     g_c.add(sum1[1]);
-    g1_compress(g_a.to_affine(), proof);                                          // :356-360 + lib.rs:39-45
+    G1X ac[2] = {g_a, g_c};                                                       // :356-360: to_affine, one inversion for A and C
+    G1Affine ac_aff[2];
+    batch_to_affine<Fp>(ac, 2, ac_aff);
+    g1_compress(ac_aff[0], proof);                                                // lib.rs:39-45
     g2_compress(g_b.to_affine(), proof + 48);
-    g1_compress(g_c.to_affine(), proof + 144);
+    g1_compress(ac_aff[1], proof + 144);
     return BB_OK;
 }
 
-int bb_groth16_prove(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, const uint8_t* r, const uint8_t* s, uint8_t* proof) {
-    if (crs && crs->shard_count != 1) { set_error("bb_groth16_prove needs an unsharded CRS; use prove_partials + finalize"); return BB_ERR_ARG; }
+}  // namespace
+
+extern "C" {
+
+int bb_groth16_prove_partials(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, uint8_t* partials) {
+    return prove_partials_impl(ctx, crs, w, partials, nullptr);
+}
+
+int bb_groth16_finalize(const bb_crs* crs, const uint8_t* partials, size_t count, const uint8_t* r_bytes, const uint8_t* s_bytes,
+                        uint8_t* proof) {
+    if (!crs || !partials || !count || !r_bytes || !s_bytes || !proof) { set_error("bb_groth16_finalize: null argument"); return BB_ERR_ARG; }
+    if (delta_is_identity(crs)) return BB_ERR_UNEXPECTED_IDENTITY;
+    Fr r, s;
+    std::memcpy(r.l, r_bytes, 32);
+    std::memcpy(s.l, s_bytes, 32);
+    ProofStatic stat;
+    finalize_static(crs, r, s, &stat);
+    return finalize_impl(crs, partials, count, r, s, stat, proof);
+}
+
+int bb_groth16_prove(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, const uint8_t* r_bytes, const uint8_t* s_bytes, uint8_t* proof) {
+    if (!crs || !r_bytes || !s_bytes || !proof) { set_error("bb_groth16_prove: null argument"); return BB_ERR_ARG; }
+    if (crs->shard_count != 1) { set_error("bb_groth16_prove needs an unsharded CRS; use prove_partials + finalize"); return BB_ERR_ARG; }
     uint8_t partials[BB_PARTIALS_BYTES];
     std::memset(partials, 0, sizeof partials);
-    BB_TRY(bb_groth16_prove_partials(ctx, crs, w, partials));
-    return bb_groth16_finalize(crs, partials, 1, r, s, proof);
+    Fr r, s;
+    std::memcpy(r.l, r_bytes, 32);
+    std::memcpy(s.l, s_bytes, 32);
+    // the five scalar multiplications that need no MSM result run on the host while the device works
+    ProofStatic stat;
+    const bool bad_delta = crs->delta_g1.is_identity() || crs->delta_g2.is_identity();
+    std::function<void()> overlap = [&] { if (!bad_delta) finalize_static(crs, r, s, &stat); };
+    BB_TRY(prove_partials_impl(ctx, crs, w, partials, &overlap));     // reports delta = identity as well (prover.rs:320-324)
+    return finalize_impl(crs, partials, 1, r, s, stat, proof);
 }
 
 }  // extern "C"

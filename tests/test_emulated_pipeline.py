@@ -147,3 +147,7 @@ def test_emulated_prove_mimc322_and_shards(worker):
             pk.free()
         assert bb.finalize(params, parts, r, s) == proof, count
 
+
+
+def test_emulated_prover_error_precedence(worker):
+    G.test_prove_error_precedence(worker)

@@ -464,3 +464,58 @@ def test_prove_synthetic_chain_trapdoor(worker, rounds):
     assert proof == mc.expected_proof(r, s)
     if rounds < 10000:
         assert proof == mc.prove(r, s)
+
+
+def test_prove_error_precedence(worker):
+    """Which SynthesisError create_proof returns when several apply (groth16/src/prover.rs): the
+    delta check (:320-324) precedes every wait; the waits run a_inputs, a_aux, b_g1_inputs,
+    b_g1_aux, b_g2_inputs, b_g2_aux, h, l (:339-354), so an identity hit in the A query is
+    reported even if the (earlier started) l multiexp ran out of bases."""
+    rng = random.Random(72)
+    mc = o1.Mimc(20, seed=5)
+    mc.set_toxic([rng.randrange(1, R) for _ in range(5)])
+    mc.generate()
+    asg = _assignment(mc.witness())
+    r, s = rng.randrange(R), rng.randrange(R)
+    good = mc.export_params()
+    proof = bb.create_proof(asg, bb.Parameters(worker, good), r, s)
+    assert proof == mc.prove(r, s)
+
+    def variant(**changes):
+        p = {k: np.array(v, copy=True) for k, v in good.items()}
+        for k, f in changes.items():
+            p[k] = f(p[k])
+        return bb.Parameters(worker, p)
+
+    def short(v):                      # drop the last base: Source::next runs out (IoError UnexpectedEof)
+        return v.reshape(-1, v.shape[-1])[:-1]
+
+    def ident(row):                    # an identity base that a non-zero scalar hits (UnexpectedIdentity)
+        def f(v):
+            v = v.reshape(-1, v.shape[-1]).copy()
+            v[row] = 0
+            return v
+        return f
+
+    with pytest.raises(bb.IoError):
+        bb.create_proof(asg, variant(l=short), r, s)
+    with pytest.raises(bb.UnexpectedIdentity):
+        bb.create_proof(asg, variant(a=ident(3)), r, s)
+    with pytest.raises(bb.UnexpectedIdentity):                    # a_aux is waited for before l
+        bb.create_proof(asg, variant(l=short, a=ident(3)), r, s)
+    with pytest.raises(bb.IoError):                               # b_g1_aux (EOF) before h (identity)
+        bb.create_proof(asg, variant(b_g1=short, h=ident(2)), r, s)
+    with pytest.raises(bb.UnexpectedIdentity):                    # h (identity) before l (EOF)
+        bb.create_proof(asg, variant(l=short, h=ident(2)), r, s)
+
+    def zero_delta(v):
+        v = v.reshape(3, -1).copy()
+        v[2] = 0
+        return v
+    with pytest.raises(bb.UnexpectedIdentity):                    # delta = identity wins over an EOF
+        bb.create_proof(asg, variant(vk_g1=zero_delta, l=short, b_g1=short), r, s)
+    with pytest.raises(bb.UnexpectedIdentity):
+        bb.create_proof(asg, variant(vk_g2=zero_delta), r, s)
+    # sharded flow: the partial-sum call reports the same error
+    with pytest.raises(bb.UnexpectedIdentity):
+        bb.prove_partials(asg, variant(vk_g1=zero_delta))
