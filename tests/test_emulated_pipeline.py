@@ -151,3 +151,7 @@ def test_emulated_prove_mimc322_and_shards(worker):
 
 def test_emulated_prover_error_precedence(worker):
     G.test_prove_error_precedence(worker)
+
+
+def test_emulated_generate_parameters(worker):
+    G.test_generate_parameters_matches_oracle(worker)

@@ -519,3 +519,79 @@ def test_prove_error_precedence(worker):
     # sharded flow: the partial-sum call reports the same error
     with pytest.raises(bb.UnexpectedIdentity):
         bb.prove_partials(asg, variant(vk_g1=zero_delta))
+
+
+# --------------------------------------------------------------------------------------------
+# parameter generation on the device (groth16/src/generator.rs)
+# --------------------------------------------------------------------------------------------
+class _AssemblyAdapter:
+    """lets an oracle-0 circuit closure synthesise into the product's KeypairAssembly"""
+
+    def __init__(self, asm):
+        self.asm = asm
+
+    def alloc(self, f):
+        from oracle.oracle0 import bellman as B
+        return B.Var(False, self.asm.alloc()[1])
+
+    def alloc_input(self, f):
+        from oracle.oracle0 import bellman as B
+        return B.Var(True, self.asm.alloc_input()[1])
+
+    def enforce(self, a, b, c):
+        conv = lambda lc: [(("input" if v.is_input else "aux", v.idx), k) for v, k in lc.terms]
+        self.asm.enforce(conv(a), conv(b), conv(c))
+
+
+def test_generate_parameters_matches_oracle(worker):
+    from bellman_b200 import generator as GEN
+    from oracle.oracle0 import bellman as B, fields as F
+    rng = random.Random(90)
+    fr = B.Bls12.fr
+    constants = [rng.randrange(R) for _ in range(5)]
+    xl, xr = rng.randrange(R), rng.randrange(R)
+    circuit = B.mimc_circuit(fr, xl, xr, constants)
+    alpha, beta, gamma, delta, tau = (rng.randrange(1, R) for _ in range(5))
+    k1, k2 = rng.randrange(1, R), rng.randrange(1, R)
+    g1, g2 = F.G1.mul(F.G1_GEN, k1), F.G2.mul(F.G2_GEN, k2)
+    want = B.generate_parameters(B.Bls12, circuit, g1, g2, alpha, beta, gamma, delta, tau)
+
+    asm = GEN.KeypairAssembly()
+    asm.alloc_input()                                          # ONE, generator.rs:188
+    circuit(_AssemblyAdapter(asm))
+    got = GEN.generate_parameters(worker, asm, alpha, beta, gamma, delta, tau, g1_scalar=k1, g2_scalar=k2)
+    assert (got["num_inputs"], got["num_aux"], got["m"]) == (want.num_inputs, want.num_aux, want.m)
+
+    def g1_ints(arr):
+        return o1.g1_to_affine_ints(np.ascontiguousarray(arr).reshape(-1, 12))
+
+    def g2_ints(arr):
+        return o1.g2_to_affine_ints(np.ascontiguousarray(arr).reshape(-1, 24))
+
+    assert g1_ints(got["vk_g1"]) == [want.alpha_g1, want.beta_g1, want.delta_g1]
+    assert g2_ints(got["vk_g2"]) == [want.beta_g2, want.gamma_g2, want.delta_g2]
+    for name, conv in (("ic", g1_ints), ("h", g1_ints), ("l", g1_ints), ("a", g1_ints), ("b_g1", g1_ints), ("b_g2", g2_ints)):
+        assert conv(got[name]) == list(getattr(want, name)), name
+    # the generated key proves: same bytes as the oracle's prover on the oracle's key
+    from bellman_b200 import params_io
+    blob = params_io.write_parameters(got)
+    params = bb.Parameters(worker, params_io.read_parameters(blob))
+    wit = B.synthesize_witness(B.Bls12, circuit)
+    r, s = rng.randrange(R), rng.randrange(R)
+    proof = B.proof_bytes(B.create_proof(B.Bls12, circuit, want, r, s))
+    asg = bb.ProvingAssignment(o1.fr_from_ints(wit.a), o1.fr_from_ints(wit.b), o1.fr_from_ints(wit.c),
+                               o1.fr_from_ints(wit.input_assignment), o1.fr_from_ints(wit.aux_assignment),
+                               wit.a_aux_density, wit.b_input_density, wit.b_aux_density)
+    assert bb.create_proof(asg, params, r, s) == proof
+    # an unconstrained auxiliary variable and a non-invertible delta are errors (generator.rs:228-243,466-470)
+    asm2 = GEN.KeypairAssembly()
+    asm2.alloc_input()
+    circuit(_AssemblyAdapter(asm2))
+    asm2.alloc()
+    with pytest.raises(GEN.UnconstrainedVariable):
+        GEN.generate_parameters(worker, asm2, alpha, beta, gamma, delta, tau)
+    asm3 = GEN.KeypairAssembly()
+    asm3.alloc_input()
+    circuit(_AssemblyAdapter(asm3))
+    with pytest.raises(bb.UnexpectedIdentity):
+        GEN.generate_parameters(worker, asm3, alpha, beta, gamma, 0, tau)
