@@ -498,12 +498,30 @@ def prove_partials(assignment, params, device_ptrs=None):
     return bytes(out)
 
 
-def finalize(params, partial_sets, r, s):
-    """prover.rs:320-360 + Proof::write; partial_sets: list of 960-byte blobs (one per shard)."""
+PROOF_STATIC_BYTES = 768
+
+
+def finalize_static(params, r, s):
+    """the terms of A, B, C that need no MSM result (prover.rs:326-337); host only, callable from a
+    thread while the devices work (ctypes releases the GIL)"""
+    out = (C.c_uint8 * PROOF_STATIC_BYTES)()
+    _check(load_library().bb_groth16_finalize_static(params._h, _scalar_bytes(r), _scalar_bytes(s), out))
+    return bytes(out)
+
+
+def finalize(params, partial_sets, r, s, static=None):
+    """prover.rs:320-360 + Proof::write; partial_sets: list of 960-byte blobs (one per shard);
+    `static`: the result of finalize_static(params, r, s) if it was computed ahead."""
     blob = b"".join(partial_sets)
     buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
     proof = (C.c_uint8 * 192)()
-    _check(load_library().bb_groth16_finalize(params._h, buf, C.c_size_t(len(partial_sets)), _scalar_bytes(r), _scalar_bytes(s), proof))
+    if static is None:
+        _check(load_library().bb_groth16_finalize(params._h, buf, C.c_size_t(len(partial_sets)), _scalar_bytes(r), _scalar_bytes(s), proof))
+    else:
+        assert len(static) == PROOF_STATIC_BYTES
+        st = (C.c_uint8 * PROOF_STATIC_BYTES).from_buffer_copy(static)
+        _check(load_library().bb_groth16_finalize_with(params._h, buf, C.c_size_t(len(partial_sets)), _scalar_bytes(r), _scalar_bytes(s),
+                                                        st, proof))
     return bytes(proof)
 
 

@@ -361,6 +361,31 @@ int bb_groth16_finalize(const bb_crs* crs, const uint8_t* partials, size_t count
     return finalize_impl(crs, partials, count, r, s, stat, proof);
 }
 
+static_assert(sizeof(ProofStatic) == BB_PROOF_STATIC_BYTES, "ProofStatic layout");
+
+int bb_groth16_finalize_static(const bb_crs* crs, const uint8_t* r_bytes, const uint8_t* s_bytes, uint8_t* static_out) {
+    if (!crs || !r_bytes || !s_bytes || !static_out) { set_error("bb_groth16_finalize_static: null argument"); return BB_ERR_ARG; }
+    Fr r, s;
+    std::memcpy(r.l, r_bytes, 32);
+    std::memcpy(s.l, s_bytes, 32);
+    ProofStatic stat;
+    finalize_static(crs, r, s, &stat);
+    std::memcpy(static_out, &stat, sizeof stat);
+    return BB_OK;
+}
+
+int bb_groth16_finalize_with(const bb_crs* crs, const uint8_t* partials, size_t count, const uint8_t* r_bytes, const uint8_t* s_bytes,
+                             const uint8_t* static_in, uint8_t* proof) {
+    if (!crs || !partials || !count || !r_bytes || !s_bytes || !static_in || !proof) { set_error("bb_groth16_finalize_with: null argument"); return BB_ERR_ARG; }
+    if (delta_is_identity(crs)) return BB_ERR_UNEXPECTED_IDENTITY;
+    Fr r, s;
+    std::memcpy(r.l, r_bytes, 32);
+    std::memcpy(s.l, s_bytes, 32);
+    ProofStatic stat;
+    std::memcpy(&stat, static_in, sizeof stat);
+    return finalize_impl(crs, partials, count, r, s, stat, proof);
+}
+
 int bb_groth16_prove(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, const uint8_t* r_bytes, const uint8_t* s_bytes, uint8_t* proof) {
     if (!crs || !r_bytes || !s_bytes || !proof) { set_error("bb_groth16_prove: null argument"); return BB_ERR_ARG; }
     if (crs->shard_count != 1) { set_error("bb_groth16_prove needs an unsharded CRS; use prove_partials + finalize"); return BB_ERR_ARG; }

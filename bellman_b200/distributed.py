@@ -50,8 +50,22 @@ def create_proof_sharded(assignment, params, full_vk_params, r, s, device_ptrs=N
     import torch
     import torch.distributed as dist
 
-    from . import BackendError, SynthesisError, _ERRORS, finalize, prove_partials
+    import threading
 
+    from . import BackendError, SynthesisError, _ERRORS, finalize, finalize_static, prove_partials
+
+    # rank 0: the scalar multiplications of the finalisation that need no MSM result run on a host
+    # thread while the devices compute the partial sums
+    ahead = {}
+    worker_thread = None
+    if dist.get_rank(group) == 0:
+        def _static():
+            try:
+                ahead["static"] = finalize_static(full_vk_params, r, s)
+            except Exception as e:                       # reported by finalize() below if it matters
+                ahead["error"] = e
+        worker_thread = threading.Thread(target=_static)
+        worker_thread.start()
     status, blob, msg = 0, bytes(PARTIALS_BYTES), ""
     try:
         blob = prove_partials(assignment, params, device_ptrs)
@@ -65,10 +79,12 @@ def create_proof_sharded(assignment, params, full_vk_params, r, s, device_ptrs=N
     out = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(out, mine, group=group)
     gathered = [bytes(t.cpu().numpy()) for t in out]
+    if worker_thread is not None:
+        worker_thread.join()
     for rank, g in enumerate(gathered):
         if g[PARTIALS_BYTES]:
             code = g[PARTIALS_BYTES]
             raise _ERRORS.get(code, BackendError)(f"rank {rank} failed with bb_status {code}" + (f": {msg}" if msg else ""))
     if dist.get_rank(group) == 0:
-        return finalize(full_vk_params, [g[:PARTIALS_BYTES] for g in gathered], r, s)
+        return finalize(full_vk_params, [g[:PARTIALS_BYTES] for g in gathered], r, s, static=ahead.get("static"))
     return None

@@ -191,6 +191,15 @@ int bb_groth16_prove_partials(bb_ctx* ctx, const bb_crs* crs, const bb_witness* 
  * (groth16/src/lib.rs:39-45).  r, s: 32-byte canonical little-endian scalars. */
 int bb_groth16_finalize(const bb_crs* crs, const uint8_t* partials, size_t count,
                         const uint8_t r[32], const uint8_t s[32], uint8_t proof[192]);
+/* The same in two steps, so that the five scalar multiplications that need no MSM result
+ * (delta*r, delta*s, delta*rs, alpha*s, beta*r -- prover.rs:326-337) can run on a host thread while
+ * the devices compute the partial sums: finalize_static fills BB_PROOF_STATIC_BYTES opaque bytes,
+ * finalize_with consumes them.  bb_groth16_finalize == finalize_static + finalize_with;
+ * bb_groth16_prove overlaps them internally. */
+#define BB_PROOF_STATIC_BYTES 768
+int bb_groth16_finalize_static(const bb_crs* crs, const uint8_t r[32], const uint8_t s[32], uint8_t* static_out);
+int bb_groth16_finalize_with(const bb_crs* crs, const uint8_t* partials, size_t count, const uint8_t r[32],
+                             const uint8_t s[32], const uint8_t* static_in, uint8_t* proof);
 /* single-GPU convenience: partials + finalize */
 int bb_groth16_prove(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w,
                      const uint8_t r[32], const uint8_t s[32], uint8_t proof[192]);

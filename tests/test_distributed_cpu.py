@@ -67,3 +67,65 @@ def test_sharded_partials_gloo_world2(tmp_path):
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert (tmp_path / "ok.0").exists() and (tmp_path / "ok.1").exists(), res.stdout + res.stderr
+
+
+SHARDED_PROVE = textwrap.dedent('''
+    import os, sys, random
+    import numpy as np
+    import torch.distributed as dist
+    sys.path.insert(0, os.environ["BB_ROOT"]); sys.path.insert(0, os.path.join(os.environ["BB_ROOT"], "tests"))
+    import bellman_b200 as bb
+    bb.LIB_PATH, bb._lib = os.environ["BB_EMU_LIB"], None            # host-fiber execution of the product sources
+    from bellman_b200.distributed import create_proof_sharded
+    from oracle import o1
+
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    R = o1.FR_MODULUS
+    rng = random.Random(5)
+    mc = o1.Mimc(40, seed=9)
+    mc.set_toxic([rng.randrange(1, R) for _ in range(5)])
+    mc.generate()
+    w = mc.witness()
+    asg = bb.ProvingAssignment(w["a"], w["b"], w["c"], w["inputs"], w["aux"], w["a_aux_density"], w["b_input_density"], w["b_aux_density"])
+    worker = bb.Worker(0)
+    mine = bb.Parameters(worker, mc.export_params(), shard_index=rank, shard_count=world)
+    r, s = rng.randrange(R), rng.randrange(R)
+    proof = create_proof_sharded(asg, mine, mine, r, s)
+    if rank == 0:
+        assert proof == mc.prove(r, s) == mc.expected_proof(r, s)
+    else:
+        assert proof is None
+    # a shard with an identity base: every rank raises the same SynthesisError
+    bad = mc.export_params()
+    if rank == 1:
+        bad["l"] = np.array(bad["l"], copy=True); bad["l"].reshape(-1, 12)[-1] = 0
+    broken = bb.Parameters(worker, bad, shard_index=rank, shard_count=world)
+    try:
+        create_proof_sharded(asg, broken, broken, r, s)
+        raise SystemExit("expected UnexpectedIdentity")
+    except bb.UnexpectedIdentity:
+        pass
+    worker.close()
+    dist.destroy_process_group()
+    open(os.path.join(os.path.dirname(os.path.abspath(__file__)), f"ok.{rank}"), "w").write("ok")
+''')
+
+
+def test_sharded_prove_gloo_world2_emulated_device(tmp_path):
+    """The whole N>1 path on CPU: two gloo ranks, each running the product sources on host fibers
+    (tests/native) over its (base range x window) shard, one all-gather, finalize on rank 0 with
+    the static terms computed on a host thread meanwhile."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tests", "native", "build_emu.py"))
+    be = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(be)
+    lib, _ = be.build(str(tmp_path / "emu"))
+    script = tmp_path / "worker.py"
+    script.write_text(SHARDED_PROVE)
+    env = dict(os.environ, BB_ROOT=ROOT, BB_EMU_LIB=lib)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29519", str(script)]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert (tmp_path / "ok.0").exists() and (tmp_path / "ok.1").exists(), res.stdout + res.stderr

@@ -146,6 +146,7 @@ def test_emulated_prove_mimc322_and_shards(worker):
             parts.append(bb.prove_partials(asg, pk))
             pk.free()
         assert bb.finalize(params, parts, r, s) == proof, count
+        assert bb.finalize(params, parts, r, s, static=bb.finalize_static(params, r, s)) == proof
 
 
 

@@ -407,6 +407,7 @@ def test_prove_mimc322_matches_oracle(worker):
             parts.append(bb.prove_partials(asg, pk))
             pk.free()
         assert bb.finalize(params, parts, r, s) == proof, count
+        assert bb.finalize(params, parts, r, s, static=bb.finalize_static(params, r, s)) == proof
     try:
         worker.set_option("shard_windows", 1)
         parts = []
