@@ -534,6 +534,15 @@ def create_proof(assignment, params, r, s, device_ptrs=None):
     return bytes(proof)
 
 
+def create_random_proof(assignment, params, rng=None, device_ptrs=None):
+    """groth16::create_random_proof (prover.rs:164-179): r, s <- Fr::random, then create_proof.
+    `rng`: anything with randrange (default: the operating system's CSPRNG)."""
+    import secrets
+    draw = rng.randrange if rng is not None else secrets.randbelow
+    q = EvaluationDomain.FR_MODULUS
+    return create_proof(assignment, params, draw(q), draw(q), device_ptrs)
+
+
 def synth_mimc(rounds, seed, pinned=False):
     """bench-only: the MiMC-chain witness of `rounds` rounds as a ProvingAssignment (product-side
     generator, bellman_b200/csrc/synth.cu).  pinned=True places the arrays in page-locked host

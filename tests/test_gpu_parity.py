@@ -384,6 +384,9 @@ def test_prove_mimc322_matches_oracle(worker):
         assert len(proof) == 192                                     # groth16/src/lib.rs:559
         assert proof == mc.prove(r, s)
         assert proof == mc.expected_proof(r, s)
+    # create_random_proof (prover.rs:164-179): fresh (r, s) every call, and the proof verifies (below)
+    rp1, rp2 = bb.create_random_proof(asg, params), bb.create_random_proof(asg, params)
+    assert len(rp1) == 192 and rp1 != rp2
     # a key that went through Parameters::write / Parameters::read (groth16/src/lib.rs:258-398)
     from bellman_b200 import params_io
     reloaded = bb.Parameters(worker, params_io.read_parameters(params_io.write_parameters(mc.export_params())))
@@ -397,6 +400,7 @@ def test_prove_mimc322_matches_oracle(worker):
     image = o1.fr_to_ints(mc.witness()["inputs"])[1]
     assert PR.verify_proof(vk, PR.proof_read(proof), [image])
     assert not PR.verify_proof(vk, PR.proof_read(proof), [image ^ 1])
+    assert PR.verify_proof(vk, PR.proof_read(rp1), [image])
     # sharded across "devices": the partial sums of the (base range x window) shards add up to the
     # same proof.  2 and 3 shards split the windows only; 8 = 2 base ranges x 4 window shards;
     # 5 has no divisor <= 4 and splits the bases only; shard_windows=1 forces base ranges alone.
