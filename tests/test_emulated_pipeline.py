@@ -199,3 +199,31 @@ def test_emulated_multiexp_fuzz(worker):
     finally:
         worker.set_option("msm_window_bits", 0)
         worker.set_option("msm_big_cap", 0)
+
+
+def test_emulated_bench_paths(worker):
+    """What bench.py times: the synthetic MiMC-chain witness, the device-generated synthetic CRS, a
+    witness already resident in device memory (`value` leg) against host buffers (`e2e` leg), and
+    the N-way synthetic shards of `--gpus N` -- all must give one and the same proof."""
+    asg, shape = bb.synth_mimc(60, seed=20)
+    assert shape["num_constraints"] == 122 and shape["m"] == 128
+    params = bb.Parameters.synthetic(worker, 21, shape)
+    r, s = 0x1234567, 0x7654321
+    p_host = bb.create_proof(asg, params, r, s)
+    assert len(p_host) == 192 and bb.create_proof(asg, params, r, s) == p_host
+    dev, bufs = {}, []
+    for name, arr in (("a", asg.a), ("b", asg.b), ("c", asg.c), ("inputs", asg.input_assignment), ("aux", asg.aux_assignment)):
+        d = worker.device_alloc(arr.nbytes)
+        worker.upload(d, arr)
+        dev[name] = d.value
+        bufs.append(d)
+    assert bb.create_proof(asg, params, r, s, dev) == p_host
+    for count in (2, 4, 8):
+        parts = []
+        for k in range(count):
+            pk = bb.Parameters.synthetic(worker, 21, shape, shard_index=k, shard_count=count)
+            parts.append(bb.prove_partials(asg, pk, dev))
+            pk.free()
+        assert bb.finalize(params, parts, r, s) == p_host, count
+    for d in bufs:
+        worker.device_free(d)
