@@ -66,6 +66,7 @@ struct bb_ctx {
         e.ms += ms; e.launches += launches; e.units += units;
     }
     std::map<uint32_t, bb::NttTables*> ntt_tables;   // by log_n
+    cudaEvent_t epoch_ev = nullptr;                  // profile mode: start of the current prove (device timeline origin)
 
     // small page-locked staging blocks for results (cudaMallocHost/cudaFreeHost synchronise the
     // device and are slow; jobs borrow fixed-size blocks instead)
@@ -125,7 +126,8 @@ struct MsmResult {
     G2X x2;
 };
 int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint64_t* density_bits, size_t density_len,
-              const void* scalars, bool scalars_on_device, size_t n, int form, cudaEvent_t wait_for, bb_msm_job** out);
+              const void* scalars, bool scalars_on_device, size_t n, int form, cudaEvent_t wait_for, bb_msm_job** out,
+              const char* tag = nullptr);
 int msm_wait_result(bb_msm_job* job, MsmResult* res);
 
 }  // namespace bb

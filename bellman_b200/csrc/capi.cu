@@ -254,6 +254,7 @@ void bb_ctx_destroy(bb_ctx* ctx) {
     for (auto p : ctx->pinned_free) cudaFreeHost(p);
     for (auto s : ctx->streams) cudaStreamDestroy(s);
     if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
+    if (ctx->epoch_ev) cudaEventDestroy(ctx->epoch_ev);
     ntt_free_tables(ctx);
     delete ctx;
 }

@@ -461,6 +461,7 @@ struct bb_msm_job {
     uint32_t W_local = 0;            // windows this device owns (all of them unless window-sharded)
     size_t n = 0;
     int status = BB_OK;              // pre-launch failure, reported at wait()
+    const char* tag = nullptr;       // profile mode: name of this job in the prover's timeline
     DigitArgs dargs{};
     DevBuf d_scalars, d_density, d_rank, d_counts, d_offsets, d_tiles, d_sorted, d_order, d_buckets, d_partials, d_runs, d_levels, d_onesp, d_final, d_ones, d_err, d_big, d_tasks, d_biglist, d_tasksums;
     std::vector<uint32_t> h_rank;
@@ -676,7 +677,8 @@ int launch_msm(bb_msm_job* job) {
 }  // namespace
 namespace bb {
 int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint64_t* density_bits, size_t density_len,
-              const void* scalars, bool scalars_on_device, size_t n, int form, cudaEvent_t wait_for, bb_msm_job** out) {
+              const void* scalars, bool scalars_on_device, size_t n, int form, cudaEvent_t wait_for, bb_msm_job** out,
+              const char* tag) {
     if (!ctx || !bases || !out || (n && !scalars)) { set_error("bb_msm: null argument"); return BB_ERR_ARG; }
     if (n >= (1ull << 31) || bases->n >= (1ull << 31)) { set_error("bb_msm: more than 2^31 terms"); return BB_ERR_ARG; }
     if (form != BB_FORM_CANONICAL && form != BB_FORM_MONTGOMERY) { set_error("bb_msm: bad form"); return BB_ERR_ARG; }
@@ -684,6 +686,7 @@ int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint
     bb_msm_job* job = new bb_msm_job();
     *out = job;
     job->ctx = ctx; job->bases = bases; job->group = bases->group; job->n = n;
+    job->tag = tag;
     job->st = ctx->pick_stream();
     if (wait_for) BB_CUDA(cudaStreamWaitEvent(job->st, wait_for, 0));
     if (density_bits && density_len != n) {                 // the assert! at multiexp.rs:324-329
@@ -816,6 +819,14 @@ int msm_wait_result(bb_msm_job* job, MsmResult* res) {
             bool g2 = job->group == BB_G2;
             job->ctx->prof_add(g2 ? "msm_accumulate_g2" : "msm_accumulate_g1", acc_ms, 1, job->n);
             job->ctx->prof_add(g2 ? "msm_total_g2" : "msm_total_g1", tot_ms, 1, job->n);
+            if (job->tag && job->ctx->epoch_ev) {            // device timeline of the prover: ms since the prove started
+                static const char* const mark[4] = {"start", "acc_start", "acc_end", "end"};
+                for (int i = 0; i < 4; i++) {
+                    float t = 0;
+                    if (cudaEventElapsedTime(&t, job->ctx->epoch_ev, job->ev[i]) == cudaSuccess)
+                        job->ctx->prof_add((std::string("tl.") + job->tag + "." + mark[i]).c_str(), t, 1, 0);
+                }
+            }
         }
         for (auto& e : job->ev) if (e) cudaEventDestroy(e);
         cudaGetLastError();

@@ -1,7 +1,9 @@
 // bellman_b200: the device side of groth16::create_proof after synthesis
 // (/root/reference/groth16/src/prover.rs:217-360): CRS residency, the H pipeline, the eight
 // multiexps in flight, and the host finalisation.
+#include <chrono>
 #include <functional>
+#include <string>
 
 #include "bb_internal.cuh"
 
@@ -197,6 +199,10 @@ int prove_partials_impl(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, uin
         if (log_m >= (uint32_t)bbc::FR_S) { set_error("PolynomialDegreeTooLarge"); return BB_ERR_POLYNOMIAL_DEGREE_TOO_LARGE; }
     }
     cudaStream_t st = ctx->main_stream;
+    if (ctx->opt_profile) {                           // origin of the per-job device timeline (bb_profile_read "tl.<job>.<mark>")
+        if (!ctx->epoch_ev) BB_CUDA(cudaEventCreate(&ctx->epoch_ev));
+        BB_CUDA(cudaEventRecord(ctx->epoch_ev, st));
+    }
     DevBuf d_a, d_b, d_c, d_tmp, d_in, d_aux;
     BB_TRY(d_a.alloc(ctx, m * 32)); BB_TRY(d_b.alloc(ctx, m * 32)); BB_TRY(d_c.alloc(ctx, m * 32)); BB_TRY(d_tmp.alloc(ctx, m * 32));
     BB_TRY(d_in.alloc(ctx, w->n_inputs * 32)); BB_TRY(d_aux.alloc(ctx, w->n_aux * 32));
@@ -219,8 +225,9 @@ int prove_partials_impl(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, uin
     }
     bb_msm_job* jobs[8] = {nullptr};
     int s = BB_OK;
+    static const char* const job_tag[8] = {"h", "l", "a_inputs", "a_aux", "b_g1_inputs", "b_g1_aux", "b_g2_inputs", "b_g2_aux"};
     auto start = [&](int slot, const bb_bases* bases, size_t off, const uint64_t* dens, size_t dens_len, const void* d_sc, size_t cnt, cudaEvent_t ev) {
-        if (s == BB_OK) s = msm_start(ctx, bases, off, dens, dens_len, d_sc, true, cnt, BB_FORM_MONTGOMERY, ev, &jobs[slot]);
+        if (s == BB_OK) s = msm_start(ctx, bases, off, dens, dens_len, d_sc, true, cnt, BB_FORM_MONTGOMERY, ev, &jobs[slot], job_tag[slot]);
     };
     start(1, crs->l, 0, nullptr, 0, d_aux.p, w->n_aux, ev_up);                                              // :263-268
     start(2, crs->a, 0, nullptr, 0, d_in.p, w->n_inputs, ev_up);                                            // :275-280
@@ -397,9 +404,25 @@ int bb_groth16_prove(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, const 
     // the five scalar multiplications that need no MSM result run on the host while the device works
     ProofStatic stat;
     const bool bad_delta = crs->delta_g1.is_identity() || crs->delta_g2.is_identity();
-    std::function<void()> overlap = [&] { if (!bad_delta) finalize_static(crs, r, s, &stat); };
+    // profile mode: host-side milestones of one prove, ms since entry (bb_profile_read "host.<mark>")
+    const auto t_entry = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count(); };
+    double t_queued = 0, t_static = 0;
+    std::function<void()> overlap = [&] {
+        t_queued = since();
+        if (!bad_delta) finalize_static(crs, r, s, &stat);
+        t_static = since();
+    };
     BB_TRY(prove_partials_impl(ctx, crs, w, partials, &overlap));     // reports delta = identity as well (prover.rs:320-324)
-    return finalize_impl(crs, partials, 1, r, s, stat, proof);
+    const double t_waited = since();
+    int rc = finalize_impl(crs, partials, 1, r, s, stat, proof);
+    if (ctx && ctx->opt_profile) {
+        ctx->prof_add("host.queued", t_queued, 1, 0);          // everything launched
+        ctx->prof_add("host.static_done", t_static, 1, 0);     // MSM-independent scalar multiplications done
+        ctx->prof_add("host.msms_done", t_waited, 1, 0);       // all eight results folded on the host
+        ctx->prof_add("host.proof_done", since(), 1, 0);
+    }
+    return rc;
 }
 
 }  // extern "C"

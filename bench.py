@@ -271,6 +271,7 @@ def run_prove(args):
     acc_ms, acc_launches, acc_units = worker.profile_read("msm_accumulate_g1")
     tot_ms, _, _ = worker.profile_read("msm_total_g1")
     acc2_ms, acc2_launches, acc2_units = worker.profile_read("msm_accumulate_g2")
+    timeline = read_timeline(worker)
     worker.set_option("profile", 0)
     log(f"value leg done: {1e3 * dt_val / args.steps:.2f} ms/step; timed region: host buffers (e2e)")
     dt_e2e, proof_e2e, _, h2d, d2h = timed(None, args.steps, max(1, args.warmup // 2))
@@ -305,7 +306,7 @@ def run_prove(args):
                 "ms_per_step": 1e3 * dt_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate<Fp> (G1 bucket accumulation)", "achieved": achieved, "peak": hbm_peak,
+        "timeline": timeline, "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate<Fp> (G1 bucket accumulation)", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
                      "traffic": (tr_pair * pairs_per_launch) if tr_pair else None, "traffic_source": tr_src,
                      "algorithmic_bytes_per_launch": 128.0 * pairs_per_launch, "peak_source": peak_src,
@@ -335,6 +336,27 @@ def run_prove(args):
     worker.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def read_timeline(worker):
+    """Per-step averages from the profile counters of the timed `value` leg: for every MSM job of the
+    prover the device times (ms since the prove was entered: job queued on its stream, bucket
+    accumulation start / end, window sums on the host side of the copy) and the host milestones of
+    bb_groth16_prove.  CUDA events on each job's own stream; N=1 path only (the sharded path reports
+    the jobs, not the host milestones)."""
+    out = {"device_ms_since_prove_start": {}, "host_ms_since_prove_start": {}}
+    for job in ("h", "l", "a_inputs", "a_aux", "b_g1_inputs", "b_g1_aux", "b_g2_inputs", "b_g2_aux"):
+        marks = []
+        for mark in ("start", "acc_start", "acc_end", "end"):
+            ms, cnt, _ = worker.profile_read(f"tl.{job}.{mark}")
+            marks.append(round(ms / cnt, 3) if cnt else None)
+        if any(m is not None for m in marks):
+            out["device_ms_since_prove_start"][job] = dict(zip(("queued", "accumulate_start", "accumulate_end", "done"), marks))
+    for mark in ("queued", "static_done", "msms_done", "proof_done"):
+        ms, cnt, _ = worker.profile_read(f"host.{mark}")
+        if cnt:
+            out["host_ms_since_prove_start"][mark] = round(ms / cnt, 3)
+    return out
 
 
 def run_msm(args):

@@ -227,3 +227,27 @@ def test_emulated_bench_paths(worker):
         assert bb.finalize(params, parts, r, s) == p_host, count
     for d in bufs:
         worker.device_free(d)
+
+
+def test_emulated_profile_timeline(worker):
+    """profile mode: the per-job device timeline and the host milestones of bb_groth16_prove that
+    bench.py reports (`timeline`); in the emulation the times are zeros, the plumbing is what is checked"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    asg, shape = bb.synth_mimc(20, seed=3)
+    params = bb.Parameters.synthetic(worker, 5, shape)
+    worker.set_option("profile", 1)
+    worker.profile_reset()
+    try:
+        for _ in range(2):
+            bb.create_proof(asg, params, 11, 13)
+        tl = bench.read_timeline(worker)
+    finally:
+        worker.set_option("profile", 0)
+    assert set(tl["device_ms_since_prove_start"]) == {"h", "l", "a_inputs", "a_aux", "b_g1_inputs", "b_g1_aux", "b_g2_inputs", "b_g2_aux"}
+    assert all(set(v) == {"queued", "accumulate_start", "accumulate_end", "done"} for v in tl["device_ms_since_prove_start"].values())
+    host = tl["host_ms_since_prove_start"]
+    assert 0 <= host["queued"] <= host["static_done"] <= host["msms_done"] <= host["proof_done"]
+    assert worker.profile_read("host.proof_done")[1] == 2
