@@ -39,3 +39,49 @@ def test_reference_arm_under_torchrun_world2():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0, res.stderr
     _check_line(res.stdout, 2)
+
+
+DRY_RUN = '''
+import importlib.util, sys
+sys.path.insert(0, ROOT)
+import torch
+torch.cuda.set_device = lambda *a, **k: None
+torch.cuda.synchronize = lambda *a, **k: None
+_to = torch.Tensor.to
+torch.Tensor.to = lambda self, *a, **k: self if (a and isinstance(a[0], str) and a[0].startswith("cuda")) else _to(self, *a, **k)
+torch.Tensor.pin_memory = lambda self, *a, **k: self
+import bellman_b200 as bb
+bb.LIB_PATH, bb._lib = EMU_LIB, None          # the product sources on host fibers (tests/native)
+spec = importlib.util.spec_from_file_location("bench", ROOT + "/bench.py")
+bench = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(bench)
+sys.argv = ["bench.py", "--log-size", "8", "--steps", "2", "--warmup", "1", "--cpu-sample-log", "8"]
+bench.main()
+'''
+
+
+def test_own_arm_dry_run_on_the_emulated_device(tmp_path):
+    """bench.py's default workload (prove: value leg, e2e leg, roofline, timeline, cpu_baseline) end
+    to end with the CUDA library replaced by the host-fiber build of the same sources and torch.cuda
+    stubbed: checks the script and the JSON contract, not the numbers."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tests", "native", "build_emu.py"))
+    be = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(be)
+    lib, _ = be.build(str(tmp_path / "emu"))
+    script = tmp_path / "dry.py"
+    script.write_text(f"ROOT = {ROOT!r}\nEMU_LIB = {lib!r}\n" + DRY_RUN)
+    res = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-3000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, res.stdout
+    d = json.loads(lines[0])
+    need = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+            "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "timeline"}
+    assert need <= set(d), need - set(d)
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1 and d["gpu_launches"] > 100
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"]) and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] == "port"
+    assert len(d["timeline"]["device_ms_since_prove_start"]) == 8
+    assert "workload" in d["config"] and "model" not in d["config"]
