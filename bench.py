@@ -394,7 +394,7 @@ def run_msm(args):
     acc_ms, acc_l, acc_u = worker.profile_read("msm_accumulate_g1")
     tot_ms, _, _ = worker.profile_read("msm_total_g1")
     hbm_peak, peak_src = peaks()
-    achieved = 128.0 * n * args.steps / (tot_ms * 1e-3) / 1e9
+    achieved = 128.0 * n * args.steps / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else None
     line = {"metric": "g1_msm_mpt_per_sec", "value": n * args.steps / dt / 1e6, "unit": "Mpt/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32 limbs", "data": "synthetic",
@@ -402,7 +402,7 @@ def run_msm(args):
                        "window_bits": args.window_bits or "auto"},
             "gpu_launches": int(worker.kernel_launches - l0), "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "whole MSM (all kernels of one job)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": (achieved / hbm_peak) if achieved else None, "traffic": None, "peak_source": peak_src,
                          "accumulate_ms": acc_ms / args.steps, "device_ms": tot_ms / args.steps, "algorithmic_bytes_per_pair": 128},
             "result_head": bytes(out[0, :2]).hex()}
     emit(line)
