@@ -274,7 +274,7 @@ def run_prove(args):
     timeline = read_timeline(worker)
     worker.set_option("profile", 0)
     log(f"value leg done: {1e3 * dt_val / args.steps:.2f} ms/step; timed region: host buffers (e2e)")
-    dt_e2e, proof_e2e, _, h2d, d2h = timed(None, args.steps, max(1, args.warmup // 2))
+    dt_e2e, proof_e2e, _, h2d, d2h = timed(None, args.steps, args.warmup)
     log(f"e2e leg done: {1e3 * dt_e2e / args.steps:.2f} ms/step")
     if rank == 0:
         assert proof_val == proof_e2e and len(proof_val) == 192
