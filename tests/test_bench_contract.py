@@ -60,17 +60,12 @@ bench.main()
 '''
 
 
-def test_own_arm_dry_run_on_the_emulated_device(tmp_path):
+def test_own_arm_dry_run_on_the_emulated_device(tmp_path, emu_lib):
     """bench.py's default workload (prove: value leg, e2e leg, roofline, timeline, cpu_baseline) end
     to end with the CUDA library replaced by the host-fiber build of the same sources and torch.cuda
     stubbed: checks the script and the JSON contract, not the numbers."""
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tests", "native", "build_emu.py"))
-    be = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(be)
-    lib, _ = be.build(str(tmp_path / "emu"))
     script = tmp_path / "dry.py"
-    script.write_text(f"ROOT = {ROOT!r}\nEMU_LIB = {lib!r}\n" + DRY_RUN)
+    script.write_text(f"ROOT = {ROOT!r}\nEMU_LIB = {emu_lib!r}\n" + DRY_RUN)
     res = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert res.returncode == 0, res.stderr[-3000:]
     lines = [l for l in res.stdout.splitlines() if l.strip()]

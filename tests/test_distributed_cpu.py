@@ -112,18 +112,13 @@ SHARDED_PROVE = textwrap.dedent('''
 ''')
 
 
-def test_sharded_prove_gloo_world2_emulated_device(tmp_path):
+def test_sharded_prove_gloo_world2_emulated_device(tmp_path, emu_lib):
     """The whole N>1 path on CPU: two gloo ranks, each running the product sources on host fibers
     (tests/native) over its (base range x window) shard, one all-gather, finalize on rank 0 with
     the static terms computed on a host thread meanwhile."""
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tests", "native", "build_emu.py"))
-    be = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(be)
-    lib, _ = be.build(str(tmp_path / "emu"))
     script = tmp_path / "worker.py"
     script.write_text(SHARDED_PROVE)
-    env = dict(os.environ, BB_ROOT=ROOT, BB_EMU_LIB=lib)
+    env = dict(os.environ, BB_ROOT=ROOT, BB_EMU_LIB=emu_lib)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29519", str(script)]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)

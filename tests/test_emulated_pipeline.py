@@ -10,7 +10,6 @@ GPU tests use (the test bodies are the ones in test_gpu_parity.py wherever their
 What it does not cover: anything nvcc/ptxas/the hardware does.  The emulated library is test
 infrastructure: it is built into a temporary directory and never loaded by the product.
 """
-import importlib.util
 import os
 import random
 
@@ -26,21 +25,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 R = o1.FR_MODULUS
 
 
-def _load_builder():
-    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tests", "native", "build_emu.py"))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    return mod
-
-
 @pytest.fixture(scope="module")
-def worker(tmp_path_factory):
-    lib = os.environ.get("BB_EMU_LIB")               # a pre-built (e.g. sanitizer) variant, see tests/native/README.md
-    if not lib:
-        lib, launches = _load_builder().build(str(tmp_path_factory.mktemp("bb_emu")))
-        assert launches >= 25
+def worker(emu_lib):
     saved = (bb.LIB_PATH, bb._lib)
-    bb.LIB_PATH, bb._lib = lib, None                 # this module only: the mirror talks to the emulated library
+    bb.LIB_PATH, bb._lib = emu_lib, None             # this module only: the mirror talks to the emulated library
     try:
         w = bb.Worker(0)
         yield w
