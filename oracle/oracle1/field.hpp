@@ -75,31 +75,33 @@ struct Mont {
     Mont neg() const { return is_zero() ? *this : (zero() - *this); }
     Mont dbl() const { return *this + *this; }
 
-    // CIOS Montgomery product  a*b*R^-1 mod p
+    // CIOS Montgomery product  a*b*R^-1 mod p.  Both moduli leave the top bit of the top limb clear,
+    // so the two inner loops of the textbook CIOS merge and no (N+2)-limb accumulator is needed
+    // (the multiplication and the reduction row share one pass; result < 2p before the final
+    // conditional subtraction).
     Mont operator*(const Mont& o) const {
-        uint64_t t[N + 2];
+        static_assert((P::MOD[N - 1] >> 63) == 0, "modulus must leave the top bit clear");
+        uint64_t t[N];
         std::memset(t, 0, sizeof t);
+#pragma GCC unroll 8
         for (int i = 0; i < N; i++) {
-            uint64_t c = 0;
-            for (int j = 0; j < N; j++) {
-                u128 s = (u128)l[j] * o.l[i] + t[j] + c;
-                t[j] = (uint64_t)s; c = (uint64_t)(s >> 64);
-            }
-            u128 s = (u128)t[N] + c;
-            t[N] = (uint64_t)s; t[N + 1] = (uint64_t)(s >> 64);
-            uint64_t m = t[0] * P::INV;
-            u128 s2 = (u128)m * P::MOD[0] + t[0];
-            c = (uint64_t)(s2 >> 64);
+            u128 p = (u128)l[0] * o.l[i] + t[0];
+            uint64_t A = (uint64_t)(p >> 64);
+            uint64_t m = (uint64_t)p * P::INV;
+            u128 q = (u128)m * P::MOD[0] + (uint64_t)p;
+            uint64_t C = (uint64_t)(q >> 64);
+#pragma GCC unroll 8
             for (int j = 1; j < N; j++) {
-                s2 = (u128)m * P::MOD[j] + t[j] + c;
-                t[j - 1] = (uint64_t)s2; c = (uint64_t)(s2 >> 64);
+                p = (u128)l[j] * o.l[i] + t[j] + A;
+                A = (uint64_t)(p >> 64);
+                q = (u128)m * P::MOD[j] + (uint64_t)p + C;
+                C = (uint64_t)(q >> 64);
+                t[j - 1] = (uint64_t)q;
             }
-            s2 = (u128)t[N] + c;
-            t[N - 1] = (uint64_t)s2;
-            t[N] = t[N + 1] + (uint64_t)(s2 >> 64);
+            t[N - 1] = C + A;
         }
         Mont r; std::memcpy(r.l, t, sizeof r.l);
-        if (t[N] || geq_mod(r.l)) sub_mod(r.l);
+        if (geq_mod(r.l)) sub_mod(r.l);
         return r;
     }
     Mont square() const { return *this * *this; }
