@@ -87,7 +87,9 @@ def rewrite(text):
     return text, count, sorted(coop)
 
 
-def build(out_dir, extra_flags=()):
+def build(out_dir, extra_flags=(), emulate_ptx=True):
+    """emulate_ptx=False compiles the kernels over mp.cuh's HOST arithmetic path (64-bit CIOS) instead of
+    the modelled PTX carry chains: the same pipeline over the other implementation of the field."""
     os.makedirs(out_dir, exist_ok=True)
     objs, launches = [], 0
     for name in SOURCES:
@@ -97,7 +99,7 @@ def build(out_dir, extra_flags=()):
         with open(cpp, "w") as f:
             f.write(src)
         obj = cpp.replace(".cpp", ".o")
-        cmd = ["g++", "-O1", "-std=c++20", "-fPIC", "-pthread", "-w", "-DBB_EMULATE_PTX", *extra_flags,
+        cmd = ["g++", "-O1", "-std=c++20", "-fPIC", "-pthread", "-w", *(["-DBB_EMULATE_PTX"] if emulate_ptx else []), *extra_flags,
                "-I", os.path.join(ROOT, "tests", "native", "cuda_emu"), "-I", CSRC, "-c", cpp, "-o", obj]
         subprocess.run(cmd, check=True)
         objs.append(obj)

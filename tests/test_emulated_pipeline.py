@@ -239,3 +239,32 @@ def test_emulated_profile_timeline(worker):
     host = tl["host_ms_since_prove_start"]
     assert 0 <= host["queued"] <= host["static_done"] <= host["msms_done"] <= host["proof_done"]
     assert worker.profile_read("host.proof_done")[1] == 2
+
+
+def test_emulated_pipeline_over_the_host_arithmetic_path(tmp_path):
+    """The same kernels compiled over mp.cuh's host arithmetic (64-bit CIOS, used by the product for
+    window folds, scalar multiplications and encodings) instead of the modelled PTX chains: both
+    implementations of the field must drive the pipeline to the same points and proofs."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tests", "native", "build_emu.py"))
+    be = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(be)
+    lib, _ = be.build(str(tmp_path / "emu_host"), emulate_ptx=False)
+    saved = (bb.LIB_PATH, bb._lib)
+    bb.LIB_PATH, bb._lib = lib, None
+    try:
+        w = bb.Worker(0)
+        G.test_field_arithmetic(w)
+        G.test_point_arithmetic(w)
+        G.test_ntt_matches_oracle(w, 9)
+        G.test_multiexp_g1_matches_oracle(w, 1000)
+        G.test_multiexp_g2_matches_oracle(w, 40)
+        rng = random.Random(3)
+        mc = o1.Mimc(30, seed=2)
+        mc.set_toxic([rng.randrange(1, R) for _ in range(5)])
+        mc.generate()
+        r, s = rng.randrange(R), rng.randrange(R)
+        assert bb.create_proof(G._assignment(mc.witness()), bb.Parameters(w, mc.export_params()), r, s) == mc.prove(r, s)
+        w.close()
+    finally:
+        bb.LIB_PATH, bb._lib = saved
