@@ -56,7 +56,15 @@ inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->multiProcessorCount = 2; std::strcpy(p->name, "host-thread emulation"); return cudaSuccess; }
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
-inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::aligned_alloc(256, (n + 255) & ~size_t(255)); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+// fresh "device memory" is filled with a poison pattern: real cudaMalloc memory holds whatever the
+// previous owner left, so a kernel that relies on zero-initialised buffers must fail here too
+inline cudaError_t cudaMalloc(void** p, size_t n) {
+    const size_t bytes = (n + 255) & ~size_t(255);
+    *p = std::aligned_alloc(256, bytes ? bytes : 256);
+    if (!*p) return cudaErrorMemoryAllocation;
+    std::memset(*p, 0xCD, bytes ? bytes : 256);
+    return cudaSuccess;
+}
 template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
 inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
 inline cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
@@ -155,7 +163,9 @@ void launch(bool cooperative, dim3 grid, dim3 block, size_t shmem, cudaStream_t,
     std::lock_guard<std::mutex> serial(S.launch_mu);           // one kernel at a time
     const unsigned nt = block.x * block.y * block.z;
     if (nt == 0 || nt > 1024 || (size_t)grid.x * grid.y * grid.z == 0) return;
-    void* sh = std::aligned_alloc(128, ((shmem ? shmem : 16) + 127) & ~size_t(127));
+    const size_t sh_bytes = ((shmem ? shmem : 16) + 127) & ~size_t(127);
+    void* sh = std::aligned_alloc(128, sh_bytes);
+    std::memset(sh, 0xCD, sh_bytes);                  // shared memory starts uninitialised on the device
     S.dyn_shared = sh;
     blockDim = {block.x, block.y, block.z};
     gridDim = {grid.x, grid.y, grid.z};
