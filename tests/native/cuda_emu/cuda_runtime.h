@@ -21,6 +21,7 @@
 #include <functional>
 #include <mutex>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 // ---- qualifiers -------------------------------------------------------------------------------
@@ -182,12 +183,16 @@ void launch(bool cooperative, dim3 grid, dim3 block, size_t shmem, cudaStream_t,
         S.obj = (void*)&fn;
         S.block = &blk;
     }
-    for (unsigned bz = 0; bz < grid.z; bz++)
-        for (unsigned by = 0; by < grid.y; by++)
-            for (unsigned bx = 0; bx < grid.x; bx++) {
+    static const bool blocks_reversed = std::getenv("BB_EMU_ORDER") != nullptr;   // blocks must be independent too
+    for (unsigned bzi = 0; bzi < grid.z; bzi++)
+        for (unsigned byi = 0; byi < grid.y; byi++)
+            for (unsigned bxi = 0; bxi < grid.x; bxi++) {
+                const unsigned bx = blocks_reversed ? grid.x - 1 - bxi : bxi, by = blocks_reversed ? grid.y - 1 - byi : byi,
+                               bz = blocks_reversed ? grid.z - 1 - bzi : bzi;
                 blockIdx = {bx, by, bz};
                 if (!cooperative) {
-                    for (unsigned t = 0; t < nt; t++) { set_thread(t); fn(); }
+                    static const bool rev = std::getenv("BB_EMU_ORDER") != nullptr;
+                    for (unsigned t = 0; t < nt; t++) { set_thread(rev ? nt - 1 - t : t); fn(); }
                     continue;
                 }
                 blk.bar.reset(nt);
@@ -201,10 +206,23 @@ void launch(bool cooperative, dim3 grid, dim3 block, size_t shmem, cudaStream_t,
                     f.ctx.uc_link = nullptr;
                     makecontext(&f.ctx, (void (*)())fiber_entry, 0);
                 }
+                // BB_EMU_ORDER=reverse|random: resume the fibers in another order between barriers; the
+                // results of a correctly synchronised kernel cannot depend on it
+                static const int order_mode = [] { const char* e = std::getenv("BB_EMU_ORDER"); return !e ? 0 : e[0] == 'r' && e[1] == 'e' ? 1 : 2; }();
+                std::vector<unsigned> order(nt);
+                for (unsigned t = 0; t < nt; t++) order[t] = order_mode == 1 ? nt - 1 - t : t;
+                if (order_mode == 2) {
+                    uint64_t x = 0x9E3779B97F4A7C15ull * (bx + 1) + by * 7919 + bz;
+                    for (unsigned t = nt - 1; t > 0; t--) {
+                        x = x * 6364136223846793005ull + 1442695040888963407ull;
+                        std::swap(order[t], order[(unsigned)((x >> 33) % (t + 1))]);
+                    }
+                }
                 unsigned remaining = nt;
                 while (remaining) {
                     bool progress = false;
-                    for (unsigned t = 0; t < nt; t++) {
+                    for (unsigned oi = 0; oi < nt; oi++) {
+                        const unsigned t = order[oi];
                         Fiber& f = fib[t];
                         if (f.done || (f.wait_bar && f.wait_bar->gen == f.wait_gen)) continue;
                         set_thread(t);
