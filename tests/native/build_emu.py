@@ -91,7 +91,7 @@ def build(out_dir, extra_flags=(), emulate_ptx=True):
     """emulate_ptx=False compiles the kernels over mp.cuh's HOST arithmetic path (64-bit CIOS) instead of
     the modelled PTX carry chains: the same pipeline over the other implementation of the field."""
     os.makedirs(out_dir, exist_ok=True)
-    objs, launches = [], 0
+    objs, launches, procs = [], 0, []
     for name in SOURCES:
         src, n, _ = rewrite(open(os.path.join(CSRC, name)).read())
         launches += n
@@ -99,10 +99,13 @@ def build(out_dir, extra_flags=(), emulate_ptx=True):
         with open(cpp, "w") as f:
             f.write(src)
         obj = cpp.replace(".cpp", ".o")
-        cmd = ["g++", "-O1", "-std=c++20", "-fPIC", "-pthread", "-w", *(["-DBB_EMULATE_PTX"] if emulate_ptx else []), *extra_flags,
+        cmd = ["g++", "-O2", "-std=c++20", "-fPIC", "-pthread", "-w", *(["-DBB_EMULATE_PTX"] if emulate_ptx else []), *extra_flags,
                "-I", os.path.join(ROOT, "tests", "native", "cuda_emu"), "-I", CSRC, "-c", cpp, "-o", obj]
-        subprocess.run(cmd, check=True)
+        procs.append((cmd, subprocess.Popen(cmd)))          # the five translation units compile side by side
         objs.append(obj)
+    for cmd, proc in procs:
+        if proc.wait() != 0:
+            raise subprocess.CalledProcessError(proc.returncode, cmd)
     lib = os.path.join(out_dir, "libbellman_b200_emu.so")
     subprocess.run(["g++", "-shared", "-pthread", *extra_flags, "-o", lib, *objs], check=True)
     return lib, launches
