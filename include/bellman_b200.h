@@ -200,7 +200,11 @@ int bb_groth16_finalize(const bb_crs* crs, const uint8_t* partials, size_t count
 int bb_groth16_finalize_static(const bb_crs* crs, const uint8_t r[32], const uint8_t s[32], uint8_t* static_out);
 int bb_groth16_finalize_with(const bb_crs* crs, const uint8_t* partials, size_t count, const uint8_t r[32],
                              const uint8_t s[32], const uint8_t* static_in, uint8_t* proof);
-/* single-GPU convenience: partials + finalize */
+/* single-GPU create_proof after synthesis (groth16/src/prover.rs:217-360): partials + finalize.
+ * When several errors apply the one the reference would return is reported: the density assert
+ * of multiexp() first (call order), then delta = identity (prover.rs:320-324, checked before any
+ * wait), then the MSM errors in the order of the reference's waits: a_inputs, a_aux,
+ * b_g1_inputs, b_g1_aux, b_g2_inputs, b_g2_aux, h, l (:339-354). */
 int bb_groth16_prove(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w,
                      const uint8_t r[32], const uint8_t s[32], uint8_t proof[192]);
 
