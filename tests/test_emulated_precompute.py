@@ -1,0 +1,52 @@
+"""MSMs over resident window multiples (bb_bases_precompute / option msm_precompute) in the host-thread
+emulation of the product sources (see test_emulated_pipeline.py): same points, same proofs, same
+error semantics as the per-window path."""
+import numpy as np
+import pytest
+
+import bellman_b200 as bb
+from oracle import o1
+
+import test_gpu_parity as G
+from test_emulated_pipeline import (worker, test_emulated_multiexp_windows,                      # noqa: F401
+                                    test_emulated_multiexp_density_fast_paths_and_skew, test_emulated_prove_mimc322_and_shards)
+
+
+@pytest.fixture()
+def precompute(worker):
+    worker.set_option("msm_precompute", 1)
+    yield worker
+    worker.set_option("msm_precompute", 0)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 33, 1000])
+def test_emulated_precompute_g1(precompute, n):
+    G.test_multiexp_g1_matches_oracle(precompute, n)
+
+
+@pytest.mark.parametrize("n", [3, 40, 300])
+def test_emulated_precompute_g2(precompute, n):
+    G.test_multiexp_g2_matches_oracle(precompute, n)
+
+
+def test_emulated_precompute_variants(precompute):
+    test_emulated_multiexp_windows(precompute)
+    test_emulated_multiexp_density_fast_paths_and_skew(precompute)
+    G.test_multiexp_error_semantics(precompute)
+    # explicit table construction, then queries of different densities / offsets over the same bases
+    n = 600
+    pts = o1.g1_fixed_mul(o1.fr_random(91, n))
+    bases = bb.Bases(precompute, bb.G1, pts).precompute()
+    rng = np.random.default_rng(9)
+    for off, m in ((0, n), (5, 200), (599, 1)):
+        dens = rng.random(m + 50) < 0.8
+        dens[np.cumsum(dens) > n - off] = False              # never run past the end
+        ex = o1.fr_random(92 + off, m + 50)
+        rc, want = o1.multiexp(1, pts, off, dens.astype(np.uint8), ex)
+        assert rc == 0
+        got = bb.multiexp(precompute, (bases, off), bb.DensityTracker(dens), ex).wait()
+        assert np.array_equal(got, want)
+
+
+def test_emulated_precompute_prove_and_shards(precompute):
+    test_emulated_prove_mimc322_and_shards(precompute)
