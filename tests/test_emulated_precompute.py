@@ -8,8 +8,8 @@ import bellman_b200 as bb
 from oracle import o1
 
 import test_gpu_parity as G
-from test_emulated_pipeline import (worker, test_emulated_multiexp_windows,                      # noqa: F401
-                                    test_emulated_multiexp_density_fast_paths_and_skew, test_emulated_prove_mimc322_and_shards)
+import test_emulated_pipeline as E
+from test_emulated_pipeline import worker                       # noqa: F401  (the emulated-library fixture)
 
 
 @pytest.fixture()
@@ -30,8 +30,8 @@ def test_emulated_precompute_g2(precompute, n):
 
 
 def test_emulated_precompute_variants(precompute):
-    test_emulated_multiexp_windows(precompute)
-    test_emulated_multiexp_density_fast_paths_and_skew(precompute)
+    E.test_emulated_multiexp_windows(precompute)
+    E.test_emulated_multiexp_density_fast_paths_and_skew(precompute)
     G.test_multiexp_error_semantics(precompute)
     # explicit table construction, then queries of different densities / offsets over the same bases
     n = 600
@@ -49,4 +49,4 @@ def test_emulated_precompute_variants(precompute):
 
 
 def test_emulated_precompute_prove_and_shards(precompute):
-    test_emulated_prove_mimc322_and_shards(precompute)
+    E.test_emulated_prove_mimc322_and_shards(precompute)
