@@ -1,0 +1,26 @@
+#!/bin/bash
+# Round-2 first GPU call: parity of the precomputed-window MSM path, then its A/B on the 2^20 prove.
+#   gpurun --timeout 900 -- 'bash tools/round2_ab.sh'
+# Results land in gpurun_out/r2_*.  Nothing here changes clocks or needs more than one GPU.
+set -u
+mkdir -p gpurun_out
+(timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -6) > gpurun_out/r2_tests.txt
+cat gpurun_out/r2_tests.txt
+run() {   # name, extra bench flags
+    local name=$1; shift
+    timeout 120 python bench.py --no-cpu-baseline "$@" > gpurun_out/r2_bench_$name.json 2> gpurun_out/r2_bench_$name.err
+    python - "$name" <<'PY'
+import json, sys
+name = sys.argv[1]
+try:
+    d = json.loads(open(f"gpurun_out/r2_bench_{name}.json").read().strip().splitlines()[-1])
+    print(f"{name:28s} value {d['ms_per_step']:7.2f} ms   e2e {d['e2e']['ms_per_step']:7.2f} ms   launches {d['gpu_launches']}")
+except Exception as e:
+    print(name, "FAILED", e)
+PY
+}
+run baseline
+run precompute --precompute 1
+for c in 14 16 17 18; do run precompute_c$c --precompute 1 --window-bits $c; done
+run baseline_bool --witness boolean
+run precompute_bool --precompute 1 --witness boolean
