@@ -272,6 +272,43 @@ __device__ __forceinline__ XYZZ<F> accumulate_range(const Affine<F>* __restrict_
     return acc;
 }
 
+// Same sum, with the next base already in flight while the current addition runs (one thread owns a
+// serial chain of ~3000 dependent instructions per addition; the gather it needs next is
+// otherwise exposed in full at only 4-8 resident warps per SM).
+template <class F>
+__device__ __forceinline__ XYZZ<F> accumulate_range_prefetch(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                             uint32_t start, uint32_t end, uint32_t* err) {
+    XYZZ<F> acc = XYZZ<F>::identity();
+    if (start >= end) return acc;
+    uint32_t v = sorted[start];
+    Affine<F> p = ld_affine(bases + (v & 0x7fffffffu));
+    for (uint32_t k = start; k < end; k++) {
+        const uint32_t vc = v;
+        Affine<F> cur = p;
+        if (k + 1 < end) {
+            v = sorted[k + 1];
+            p = ld_affine(bases + (v & 0x7fffffffu));
+        }
+        if (cur.is_identity()) { err[1] = 1; continue; }             // Source::next, multiexp.rs:63-65
+        if (vc >> 31) cur.y = cur.y.neg();
+        acc.add_mixed(cur);
+    }
+    return acc;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_accumulate_prefetch(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ offsets,
+                                                                 const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ order,
+                                                                 XYZZ<F>* buckets, size_t nb, uint32_t cap, uint32_t* err) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb) return;
+    const uint32_t b = order[t];
+    uint32_t start = offsets[b], end = offsets[b + 1];
+    if (end - start > cap) return;
+    XYZZ<F> acc = accumulate_range_prefetch<F>(bases, sorted, start, end, err);
+    st_words(buckets + b, acc);
+}
+
 template <class F, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ offsets,
                                                         const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ order,
@@ -700,6 +737,7 @@ int launch_msm(bb_msm_job* job) {
     if (prof) BB_CUDA(cudaEventRecord(job->ev[1], st));
     if (ctx->opt_msm_acc_variant == 1) k_msm_accumulate<F, 4><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
     else if (ctx->opt_msm_acc_variant == 2) k_msm_accumulate<F, 5><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
+    else if (ctx->opt_msm_acc_variant == 3) k_msm_accumulate_prefetch<F><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
     else k_msm_accumulate<F, 1><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
     {
         unsigned tgrid = (unsigned)((max_tasks + 127) / 128);

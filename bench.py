@@ -211,6 +211,8 @@ def run_prove(args):
         worker.set_option("msm_reduce_k1", args.reduce_k1)
     if args.precompute:
         worker.set_option("msm_precompute", 1)
+    if args.acc_variant:
+        worker.set_option("msm_acc_variant", args.acc_variant)
     log("synthesising the MiMC-chain witness (CPU, product-side generator)")
     asg, shape = bb.synth_mimc(rounds, seed=20, pinned=True)
     assert shape["num_constraints"] == 1 << log_n == shape["m"]

@@ -50,3 +50,18 @@ def test_emulated_precompute_variants(precompute):
 
 def test_emulated_precompute_prove_and_shards(precompute):
     E.test_emulated_prove_mimc322_and_shards(precompute)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_emulated_accumulate_variants(worker, variant):
+    """msm_acc_variant: 1, 2 = launch-bound variants, 3 = next base prefetched during the addition"""
+    worker.set_option("msm_acc_variant", variant)
+    try:
+        for pre in (0, 1):
+            worker.set_option("msm_precompute", pre)
+            G.test_multiexp_g1_matches_oracle(worker, 1000)
+            G.test_multiexp_g2_matches_oracle(worker, 40)
+            G.test_multiexp_error_semantics(worker)
+    finally:
+        worker.set_option("msm_acc_variant", 0)
+        worker.set_option("msm_precompute", 0)

@@ -22,5 +22,7 @@ PY
 run baseline
 run precompute --precompute 1
 for c in 14 16 17 18; do run precompute_c$c --precompute 1 --window-bits $c; done
+run prefetch --acc-variant 3
+run precompute_prefetch --precompute 1 --acc-variant 3
 run baseline_bool --witness boolean
 run precompute_bool --precompute 1 --witness boolean
