@@ -735,9 +735,13 @@ int launch_msm(bb_msm_job* job) {
     const size_t sh_pt = 128 * sizeof(XYZZ<F>);
     if (sh_pt > 48 * 1024) BB_CUDA(cudaFuncSetAttribute(k_msm_merge_big<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_pt));
     if (prof) BB_CUDA(cudaEventRecord(job->ev[1], st));
-    if (ctx->opt_msm_acc_variant == 1) k_msm_accumulate<F, 4><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
-    else if (ctx->opt_msm_acc_variant == 2) k_msm_accumulate<F, 5><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
-    else if (ctx->opt_msm_acc_variant == 3) k_msm_accumulate_prefetch<F><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
+    // msm_acc_variant = g1 + 10 * g2 (a tuning knob for A/B runs; results never depend on it):
+    // 0 default, 1 / 2 / 4 = 4 / 5 / 3 CTAs per SM through launch bounds, 3 = prefetching loop
+    const int acc_variant = job->group == BB_G2 ? (int)(ctx->opt_msm_acc_variant / 10) % 10 : (int)(ctx->opt_msm_acc_variant % 10);
+    if (acc_variant == 1) k_msm_accumulate<F, 4><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
+    else if (acc_variant == 2) k_msm_accumulate<F, 5><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
+    else if (acc_variant == 4) k_msm_accumulate<F, 3><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);   // G1: 160 registers, no spills, 12 warps per SM
+    else if (acc_variant == 3) k_msm_accumulate_prefetch<F><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
     else k_msm_accumulate<F, 1><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
     {
         unsigned tgrid = (unsigned)((max_tasks + 127) / 128);

@@ -52,9 +52,9 @@ def test_emulated_precompute_prove_and_shards(precompute):
     E.test_emulated_prove_mimc322_and_shards(precompute)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [11, 22, 33, 44, 4, 30])
 def test_emulated_accumulate_variants(worker, variant):
-    """msm_acc_variant: 1, 2 = launch-bound variants, 3 = next base prefetched during the addition"""
+    """msm_acc_variant = g1 + 10 * g2: 1, 2, 4 = launch-bound variants (4 / 5 / 3 CTAs per SM), 3 = next base prefetched during the addition"""
     worker.set_option("msm_acc_variant", variant)
     try:
         for pre in (0, 1):

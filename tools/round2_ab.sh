@@ -22,7 +22,7 @@ PY
 run baseline
 run precompute --precompute 1
 for c in 14 16 17 18; do run precompute_c$c --precompute 1 --window-bits $c; done
-run prefetch --acc-variant 3
-run precompute_prefetch --precompute 1 --acc-variant 3
+for v in 4 44 1 3 33 40; do run acc$v --acc-variant $v; done   # g1 + 10*g2: 4 = 3 CTAs/SM, 1 = 4 CTAs/SM, 3 = prefetch
+run precompute_acc4 --precompute 1 --acc-variant 4
 run baseline_bool --witness boolean
 run precompute_bool --precompute 1 --witness boolean
