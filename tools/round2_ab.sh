@@ -1,10 +1,10 @@
 #!/bin/bash
 # Round-2 first GPU call: parity of the precomputed-window MSM path, then its A/B on the 2^20 prove.
-#   gpurun --timeout 900 -- 'bash tools/round2_ab.sh'
+#   gpurun --timeout 1500 -- 'bash tools/round2_ab.sh'
 # Results land in gpurun_out/r2_*.  Nothing here changes clocks or needs more than one GPU.
 set -u
 mkdir -p gpurun_out
-(timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -6) > gpurun_out/r2_tests.txt
+(timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -6) > gpurun_out/r2_tests.txt
 cat gpurun_out/r2_tests.txt
 run() {   # name, extra bench flags
     local name=$1; shift
@@ -26,3 +26,5 @@ for v in 4 44 1 3 33 40; do run acc$v --acc-variant $v; done   # g1 + 10*g2: 4 =
 run precompute_acc4 --precompute 1 --acc-variant 4
 run baseline_bool --witness boolean
 run precompute_bool --precompute 1 --witness boolean
+# device timeline of the baseline and of the precomputed-window run
+for n in baseline precompute; do python tools/timeline_report.py gpurun_out/r2_bench_$n.json > gpurun_out/r2_timeline_$n.txt 2>&1; cat gpurun_out/r2_timeline_$n.txt; done
