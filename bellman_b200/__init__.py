@@ -192,6 +192,11 @@ class Bases:
         worker._children.add(self)
         return self
 
+    def precompute(self):
+        """resident window multiples 2^(c w) P_i: one bucket set for all windows (bb_bases_precompute)"""
+        _check(load_library().bb_bases_precompute(self.worker._h, self._h))
+        return self
+
     def free(self):
         if getattr(self, "_h", None):
             load_library().bb_bases_free(self._h)

@@ -58,6 +58,7 @@ struct bb_ctx {
     long opt_msm_reduce_k1 = 16;
     long opt_msm_big_cap = 0;
     long opt_shard_windows = 4;      // multi-GPU: up to this many window shards per base range (1 = base ranges only)
+    long opt_msm_precompute = 0;     // resident window multiples 2^(c w) P of every base vector (msm.cu: bases_build_table)
     struct ProfEntry { double ms = 0; uint64_t launches = 0, units = 0; };
     std::map<std::string, ProfEntry> prof;
     void prof_add(const char* what, double ms, uint64_t launches, uint64_t units) {
@@ -89,6 +90,11 @@ struct bb_bases {
     size_t global_len;       // length of the whole (unsharded) vector
     uint32_t win_index = 0;  // window shard: this device accumulates windows w % win_count == win_index
     uint32_t win_count = 1;
+    // Optional table of window multiples: slot s = w / win_count of every owned window w holds
+    // 2^(tab_c * w) * P_i at d_table[s * n + i] (affine).  With it all windows share one bucket set.
+    void* d_table = nullptr;
+    uint32_t tab_c = 0, tab_W = 0, tab_slots = 0;
+    std::mutex tab_mu;
 };
 
 namespace bb {
@@ -129,5 +135,6 @@ int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint
               const void* scalars, bool scalars_on_device, size_t n, int form, cudaEvent_t wait_for, bb_msm_job** out,
               const char* tag = nullptr);
 int msm_wait_result(bb_msm_job* job, MsmResult* res);
+int bases_build_table(bb_ctx* ctx, bb_bases* bases);
 
 }  // namespace bb

@@ -268,6 +268,7 @@ int bb_ctx_set_option(bb_ctx* ctx, const char* key, long value) {
     else if (k == "profile") ctx->opt_profile = value;
     else if (k == "msm_acc_variant") ctx->opt_msm_acc_variant = value;
     else if (k == "msm_big_cap") ctx->opt_msm_big_cap = value;
+    else if (k == "msm_precompute") ctx->opt_msm_precompute = value;
     else if (k == "shard_windows") { if (value < 1) { set_error("shard_windows >= 1"); return BB_ERR_ARG; } ctx->opt_shard_windows = value; }
     else if (k == "msm_reduce_k1") { if (value < 2 || (value & (value - 1))) { set_error("msm_reduce_k1 must be a power of two >= 2"); return BB_ERR_ARG; } ctx->opt_msm_reduce_k1 = value; }
     else if (k == "msm_reduce_k") { if (value < 2 || (value & (value - 1))) { set_error("msm_reduce_k must be a power of two >= 2"); return BB_ERR_ARG; } ctx->opt_msm_reduce_k = value; }
@@ -429,6 +430,7 @@ int bb_bases_upload(bb_ctx* ctx, int group, const void* affine, size_t n, size_t
 void bb_bases_free(bb_bases* b) {
     if (!b) return;
     if (b->d_points) b->ctx->release(b->d_points);
+    if (b->d_table) b->ctx->release(b->d_table);
     delete b;
 }
 

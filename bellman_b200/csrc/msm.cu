@@ -79,6 +79,7 @@ struct DigitArgs {
     uint64_t global_len;
     uint32_t c, W;
     uint32_t win_index, win_count;  // this device owns windows w with w % win_count == win_index
+    uint32_t table_stride;          // precomputed window multiples: entry of window slot s is base index + s * stride; 0 = none
     uint32_t* counts;               // mode 0: histogram; mode 1: cursors
     uint32_t* sorted;               // mode 1
     uint32_t* ones_list;            // base indices with scalar == 1
@@ -131,9 +132,10 @@ __global__ void __launch_bounds__(256) k_msm_digits(DigitArgs A) {
         if (raw > D) { mag = (1u << A.c) - raw; neg = 1; carry = 1; }
         else { mag = raw; neg = 0; carry = 0; }
         if (mag == 0 || w % A.win_count != A.win_index) continue;   // the carry chain runs over all windows
-        uint32_t key = (w / A.win_count) * D + (mag - 1);
+        const uint32_t slot = w / A.win_count;
+        uint32_t key = slot * D + (mag - 1);
         if (A.mode == 0) atomicAdd(&A.counts[key], 1u);
-        else A.sorted[atomicAdd(&A.counts[key], 1u)] = local | (neg << 31);
+        else A.sorted[atomicAdd(&A.counts[key], 1u)] = (local + slot * A.table_stride) | (neg << 31);
     }
 }
 
@@ -268,6 +270,43 @@ __device__ __forceinline__ XYZZ<F> accumulate_range(const Affine<F>* __restrict_
         acc.add_mixed(p);
     }
     return acc;
+}
+
+// Same sum, with the next base already in flight while the current addition runs (one thread owns a
+// serial chain of ~3000 dependent instructions per addition; the gather it needs next is
+// otherwise exposed in full at only 4-8 resident warps per SM).
+template <class F>
+__device__ __forceinline__ XYZZ<F> accumulate_range_prefetch(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                             uint32_t start, uint32_t end, uint32_t* err) {
+    XYZZ<F> acc = XYZZ<F>::identity();
+    if (start >= end) return acc;
+    uint32_t v = sorted[start];
+    Affine<F> p = ld_affine(bases + (v & 0x7fffffffu));
+    for (uint32_t k = start; k < end; k++) {
+        const uint32_t vc = v;
+        Affine<F> cur = p;
+        if (k + 1 < end) {
+            v = sorted[k + 1];
+            p = ld_affine(bases + (v & 0x7fffffffu));
+        }
+        if (cur.is_identity()) { err[1] = 1; continue; }             // Source::next, multiexp.rs:63-65
+        if (vc >> 31) cur.y = cur.y.neg();
+        acc.add_mixed(cur);
+    }
+    return acc;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_accumulate_prefetch(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ offsets,
+                                                                 const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ order,
+                                                                 XYZZ<F>* buckets, size_t nb, uint32_t cap, uint32_t* err) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb) return;
+    const uint32_t b = order[t];
+    uint32_t start = offsets[b], end = offsets[b + 1];
+    if (end - start > cap) return;
+    XYZZ<F> acc = accumulate_range_prefetch<F>(bases, sorted, start, end, err);
+    st_words(buckets + b, acc);
 }
 
 template <class F, int MINB>
@@ -418,6 +457,60 @@ __global__ void __launch_bounds__(32) k_msm_reduce_combine(const XYZZ<F>* level_
     st_words(out + w, s);
 }
 
+// ---- precomputed window multiples ---------------------------------------------------------------
+// The CRS is fixed and 180 GB of HBM is mostly empty, so every base vector can keep
+// T[s][i] = 2^(c w_s) P_i for each window it owns.  A digit of window w then selects T[w][i] and all
+// windows accumulate into buckets of the SAME weights: after the per-window accumulation the
+// bucket arrays are added slot-wise (k_msm_fold_slots) and the summation by parts and the Horner
+// fold run once instead of W times.
+template <class F>
+__global__ void __launch_bounds__(128) k_table_multiples(const Affine<F>* __restrict__ pts, size_t n, uint32_t c, uint32_t W,
+                                                         uint32_t wi, uint32_t wc, XYZZ<F>* scratch) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    XYZZ<F> cur = XYZZ<F>::from_affine(ld_affine(pts + i));
+    for (uint32_t w = 0; w < W; w++) {
+        if (w % wc == wi) st_words(scratch + (size_t)(w / wc) * n + i, cur);
+        if (w + 1 < W)
+            for (uint32_t k = 0; k < c; k++) cur = cur.dbl();
+    }
+}
+// scratch (XYZZ) -> table (affine): one inversion per thread shared by its `slots` points
+// (Montgomery's trick; the prefix products are parked in the x slot of the output)
+template <class F>
+__global__ void __launch_bounds__(128) k_table_normalize(const XYZZ<F>* __restrict__ scratch, size_t n, uint32_t slots, Affine<F>* table,
+                                                         size_t table_n, size_t table_off) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F acc = FieldOps<F>::one();
+    for (uint32_t s = 0; s < slots; s++) {
+        F z = ld_words(&scratch[(size_t)s * n + i].ZZZ);
+        st_words(&table[(size_t)s * table_n + table_off + i].x, acc);
+        if (!z.is_zero()) acc = acc * z;
+    }
+    F inv = FieldOps<F>::inv(acc);
+    for (int s = (int)slots - 1; s >= 0; s--) {
+        XYZZ<F> P = ld_words(scratch + (size_t)s * n + i);
+        Affine<F>* dst = table + (size_t)s * table_n + table_off + i;
+        if (P.is_identity()) { st_words(dst, Affine<F>::identity()); continue; }
+        F pre = ld_words(&dst->x);
+        F zi3 = inv * pre;
+        inv = inv * P.ZZZ;
+        F zi2 = (zi3 * P.ZZ).sqr();
+        Affine<F> a{P.X * zi2, P.Y * zi3};
+        st_words(dst, a);
+    }
+}
+// buckets[0][d] += buckets[1][d] + ... + buckets[slots-1][d]
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_fold_slots(XYZZ<F>* buckets, uint32_t slots, uint32_t D) {
+    uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    XYZZ<F> acc = ld_words(buckets + d);
+    for (uint32_t s = 1; s < slots; s++) acc.add(ld_words(buckets + (size_t)s * D + d));
+    st_words(buckets + d, acc);
+}
+
 // Error classification when BOTH an EOF and an identity base were seen: the reference folds
 // window results from the top window down (multiexp.rs:295-300), so the error reported is the
 // top window's, and that window raises UnexpectedIdentity only for an identity base whose
@@ -459,6 +552,8 @@ struct bb_msm_job {
     int group = BB_G1;
     uint32_t c = 0, W = 0, D = 0;   // W = windows of the whole scalar
     uint32_t W_local = 0;            // windows this device owns (all of them unless window-sharded)
+    uint32_t W_out = 0;              // window sums copied back: W_local, or 1 with precomputed window multiples
+    bool precomp = false;
     size_t n = 0;
     int status = BB_OK;              // pre-launch failure, reported at wait()
     const char* tag = nullptr;       // profile mode: name of this job in the prover's timeline
@@ -609,7 +704,7 @@ int launch_msm(bb_msm_job* job) {
         ctx->count_launch();
     }
     BB_STAGE("scatter");
-    const Affine<F>* bases = (const Affine<F>*)job->bases->d_points;
+    const Affine<F>* bases = (const Affine<F>*)(job->precomp ? job->bases->d_table : job->bases->d_points);
     XYZZ<F>* buckets = job->d_buckets.as<XYZZ<F>>();
     uint32_t* order = job->d_order.as<uint32_t>();
     uint32_t* size_hist = order + NB;
@@ -640,8 +735,13 @@ int launch_msm(bb_msm_job* job) {
     const size_t sh_pt = 128 * sizeof(XYZZ<F>);
     if (sh_pt > 48 * 1024) BB_CUDA(cudaFuncSetAttribute(k_msm_merge_big<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_pt));
     if (prof) BB_CUDA(cudaEventRecord(job->ev[1], st));
-    if (ctx->opt_msm_acc_variant == 1) k_msm_accumulate<F, 4><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
-    else if (ctx->opt_msm_acc_variant == 2) k_msm_accumulate<F, 5><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
+    // msm_acc_variant = g1 + 10 * g2 (a tuning knob for A/B runs; results never depend on it):
+    // 0 default, 1 / 2 / 4 = 4 / 5 / 3 CTAs per SM through launch bounds, 3 = prefetching loop
+    const int acc_variant = job->group == BB_G2 ? (int)(ctx->opt_msm_acc_variant / 10) % 10 : (int)(ctx->opt_msm_acc_variant % 10);
+    if (acc_variant == 1) k_msm_accumulate<F, 4><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
+    else if (acc_variant == 2) k_msm_accumulate<F, 5><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
+    else if (acc_variant == 4) k_msm_accumulate<F, 3><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);   // G1: 160 registers, no spills, 12 warps per SM
+    else if (acc_variant == 3) k_msm_accumulate_prefetch<F><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
     else k_msm_accumulate<F, 1><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
     {
         unsigned tgrid = (unsigned)((max_tasks + 127) / 128);
@@ -654,17 +754,24 @@ int launch_msm(bb_msm_job* job) {
     if (prof) BB_CUDA(cudaEventRecord(job->ev[2], st));
     BB_STAGE("accumulate");
     XYZZ<F>* fin = job->d_final.as<XYZZ<F>>();
-    BB_TRY(reduce_buckets<F>(ctx, st, buckets, W, D, (uint32_t)ctx->opt_msm_reduce_k, (uint32_t)ctx->opt_msm_reduce_k1, job->d_runs, job->d_partials, job->d_levels, fin));
+    uint32_t Wr = W;                                   // window sums the reduction produces
+    if (job->precomp) {
+        if (W > 1) { k_msm_fold_slots<F><<<cdiv(D, 128), 128, 0, st>>>(buckets, W, D); ctx->count_launch(); }
+        Wr = 1;
+        BB_STAGE("fold slots");
+    }
+    job->W_out = Wr;
+    BB_TRY(reduce_buckets<F>(ctx, st, buckets, Wr, D, (uint32_t)ctx->opt_msm_reduce_k, (uint32_t)ctx->opt_msm_reduce_k1, job->d_runs, job->d_partials, job->d_levels, fin));
     size_t sh = 128 * sizeof(XYZZ<F>);
     if (sh > 48 * 1024) BB_CUDA(cudaFuncSetAttribute(k_msm_sum_list<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
     BB_TRY(job->d_onesp.alloc(ctx, ONES_BLOCKS * sizeof(XYZZ<F>)));
     XYZZ<F>* ones_partials = job->d_onesp.as<XYZZ<F>>();
     k_msm_sum_list<F><<<ONES_BLOCKS, 128, sh, st>>>(bases, A.ones_list, A.ones_count, ones_partials, A.err);
-    k_point_tree_sum<F><<<1, 128, sh, st>>>(ones_partials, ONES_BLOCKS, fin + W);
+    k_point_tree_sum<F><<<1, 128, sh, st>>>(ones_partials, ONES_BLOCKS, fin + Wr);
     ctx->count_launch(2);
     BB_STAGE("reduce");
     BB_CUDA(cudaGetLastError());
-    size_t pts = (size_t)(W + 1) * sizeof(XYZZ<F>);
+    size_t pts = (size_t)(Wr + 1) * sizeof(XYZZ<F>);
     job->h_out_bytes = pts + 16;
     BB_TRY(ctx->pinned_acquire(job->h_out_bytes, &job->h_out));
     BB_CUDA(cudaMemcpyAsync(job->h_out, fin, pts, cudaMemcpyDeviceToHost, st));
@@ -675,6 +782,49 @@ int launch_msm(bb_msm_job* job) {
 }
 
 }  // namespace
+
+namespace {
+template <class F>
+int build_table_t(bb_ctx* ctx, bb_bases* b, uint32_t c, uint32_t W, uint32_t slots) {
+    const size_t n = b->n;
+    void* table = nullptr;
+    BB_TRY(ctx->alloc((size_t)slots * n * sizeof(Affine<F>), &table));
+    // scratch in chunks of bases: slots * chunk XYZZ points (<= ~1 GB)
+    size_t chunk = (size_t(1) << 30) / ((size_t)slots * sizeof(XYZZ<F>));
+    if (chunk > n) chunk = n;
+    if (chunk < 128) chunk = 128;
+    DevBuf scratch;
+    int s = scratch.alloc(ctx, (size_t)slots * chunk * sizeof(XYZZ<F>));
+    cudaStream_t st = ctx->main_stream;
+    for (size_t lo = 0; s == BB_OK && lo < n; lo += chunk) {
+        size_t len = n - lo < chunk ? n - lo : chunk;
+        k_table_multiples<F><<<cdiv(len, 128), 128, 0, st>>>((const Affine<F>*)b->d_points + lo, len, c, W, b->win_index, b->win_count, scratch.as<XYZZ<F>>());
+        k_table_normalize<F><<<cdiv(len, 128), 128, 0, st>>>(scratch.as<XYZZ<F>>(), len, slots, (Affine<F>*)table, n, lo);
+        ctx->count_launch(2);
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { set_error("window-multiple table: kernel failed"); s = BB_ERR_CUDA; }
+    }
+    if (s != BB_OK) { ctx->release(table); return s; }
+    b->d_table = table; b->tab_c = c; b->tab_W = W; b->tab_slots = slots;
+    return BB_OK;
+}
+}  // namespace
+
+namespace bb {
+// Builds the window-multiple table of a base vector for the window size its length selects (the
+// window of an MSM over these bases is then fixed, whatever the density of the query).
+int bases_build_table(bb_ctx* ctx, bb_bases* b) {
+    std::lock_guard<std::mutex> g(b->tab_mu);
+    if (b->d_table || !b->n) return BB_OK;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    const uint32_t c = choose_window(ctx, b->n);
+    const uint32_t W = 255 / c + 1, wc = b->win_count ? b->win_count : 1;
+    uint32_t slots = 0;
+    for (uint32_t w = 0; w < W; w++) slots += (w % wc == b->win_index);
+    if (slots == 0) slots = 1;
+    if ((uint64_t)slots * b->n >= (1ull << 31)) { set_error("window-multiple table: %u slots x %zu bases exceed 2^31 entries", slots, b->n); return BB_ERR_ARG; }
+    return b->group == BB_G1 ? build_table_t<Fp>(ctx, b, c, W, slots) : build_table_t<Fp2>(ctx, b, c, W, slots);
+}
+}  // namespace bb
 namespace bb {
 int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint64_t* density_bits, size_t density_len,
               const void* scalars, bool scalars_on_device, size_t n, int form, cudaEvent_t wait_for, bb_msm_job** out,
@@ -695,7 +845,12 @@ int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint
         return BB_OK;
     }
     // the pairs this device accumulates: all scalars on one GPU, about one shard's worth when sharded
-    job->c = choose_window(ctx, n < bases->n + 1 ? n : bases->n + 1);
+    if (ctx->opt_msm_precompute && bases->n && !bases->d_table) {
+        int ts = bases_build_table(ctx, const_cast<bb_bases*>(bases));     // first use; bb_bases_precompute does it up front
+        if (ts != BB_OK) { job->status = ts; return BB_OK; }
+    }
+    job->precomp = bases->d_table != nullptr;
+    job->c = job->precomp ? bases->tab_c : choose_window(ctx, n < bases->n + 1 ? n : bases->n + 1);
     job->W = 255 / job->c + 1;
     job->D = 1u << (job->c - 1);
     auto fail = [&](int s) { job->status = s; return BB_OK; };
@@ -705,6 +860,7 @@ int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint
     A.shard_lo = bases->global_offset; A.shard_n = bases->n; A.global_len = bases->global_len;
     A.c = job->c; A.W = job->W;
     A.win_index = bases->win_index; A.win_count = bases->win_count ? bases->win_count : 1;
+    A.table_stride = job->precomp ? (uint32_t)bases->n : 0u;
     if (A.win_index >= A.win_count) { set_error("bb_msm: window shard %u of %u", A.win_index, A.win_count); return fail(BB_ERR_ARG); }
     job->W_local = 0;
     for (uint32_t w = 0; w < job->W; w++) job->W_local += (w % A.win_count == A.win_index);
@@ -791,7 +947,7 @@ int msm_wait_result(bb_msm_job* job, MsmResult* res) {
     }
     if (status == BB_OK) {
         bool g2 = job->group == BB_G2;
-        size_t pts = (size_t)(job->W_local + 1) * (g2 ? sizeof(G2X) : sizeof(G1X));
+        size_t pts = (size_t)(job->W_out + 1) * (g2 ? sizeof(G2X) : sizeof(G1X));
         const uint32_t* err = (const uint32_t*)((char*)job->h_out + pts);
         bool eof = err[0] != 0xffffffffu, ident = err[1] != 0;
         if (eof && ident) {
@@ -807,7 +963,10 @@ int msm_wait_result(bb_msm_job* job, MsmResult* res) {
         if (status == BB_OK) {
             res->g2 = g2;
             const uint32_t wi = job->dargs.win_index, wc = job->dargs.win_count;
-            if (g2) res->x2 = fold_windows<Fp2>((const G2X*)job->h_out, job->W, job->W_local, job->c, wi, wc);
+            if (job->precomp) {                       // one window sum (weights already in the table) + the ones sum
+                if (g2) { res->x2 = ((const G2X*)job->h_out)[0]; res->x2.add(((const G2X*)job->h_out)[1]); }
+                else { res->g1 = ((const G1X*)job->h_out)[0]; res->g1.add(((const G1X*)job->h_out)[1]); }
+            } else if (g2) res->x2 = fold_windows<Fp2>((const G2X*)job->h_out, job->W, job->W_local, job->c, wi, wc);
             else res->g1 = fold_windows<Fp>((const G1X*)job->h_out, job->W, job->W_local, job->c, wi, wc);
         }
     }
@@ -846,6 +1005,10 @@ int bb_msm_async(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const u
 int bb_msm_async_device(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint64_t* density_bits, size_t density_len,
                         const void* d_scalars, size_t n_scalars, int form, bb_msm_job** out) {
     return msm_start(ctx, bases, base_offset, density_bits, density_len, d_scalars, true, n_scalars, form, nullptr, out);
+}
+int bb_bases_precompute(bb_ctx* ctx, bb_bases* bases) {
+    if (!ctx || !bases || bases->ctx != ctx) { set_error("bb_bases_precompute: bad argument"); return BB_ERR_ARG; }
+    return bases_build_table(ctx, bases);
 }
 int bb_msm_wait(bb_msm_job* job, void* out_affine) {
     if (!job || !out_affine) { set_error("bb_msm_wait: null argument"); return BB_ERR_ARG; }

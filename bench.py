@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--cpu-sample-log", type=int, default=16, help="log2 constraints of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--window-bits", type=int, default=0)
+    ap.add_argument("--precompute", type=int, default=0, help="1 = resident window multiples of every base vector (msm_precompute)")
     ap.add_argument("--acc-variant", type=int, default=0)
     ap.add_argument("--reduce-k", type=int, default=0)
     ap.add_argument("--reduce-k1", type=int, default=0)
@@ -208,6 +209,10 @@ def run_prove(args):
         worker.set_option("msm_reduce_k", args.reduce_k)
     if args.reduce_k1:
         worker.set_option("msm_reduce_k1", args.reduce_k1)
+    if args.precompute:
+        worker.set_option("msm_precompute", 1)
+    if args.acc_variant:
+        worker.set_option("msm_acc_variant", args.acc_variant)
     log("synthesising the MiMC-chain witness (CPU, product-side generator)")
     asg, shape = bb.synth_mimc(rounds, seed=20, pinned=True)
     assert shape["num_constraints"] == 1 << log_n == shape["m"]
@@ -371,6 +376,8 @@ def run_msm(args):
     worker.set_option("msm_acc_variant", args.acc_variant)
     if args.reduce_k:
         worker.set_option("msm_reduce_k", args.reduce_k)
+    if args.precompute:
+        worker.set_option("msm_precompute", 1)
     log("generating bases and scalars on the device")
     bases = bb.Bases.synthetic(worker, bb.G1, 31, n)
     d_sc = worker.device_alloc(n * 32)

@@ -68,7 +68,8 @@ int bb_version(void);
 int bb_ctx_create(int device, bb_ctx** out);
 void bb_ctx_destroy(bb_ctx* ctx);
 /* tuning knobs; results never depend on them.  Known keys: "msm_window_bits" (0 = auto),
- * "ntt_tile_log" , "ntt_col_bits". */
+ * "msm_precompute" (1 = keep window multiples of every base vector resident, see
+ * bb_bases_precompute), "ntt_tile_log" , "ntt_col_bits". */
 int bb_ctx_set_option(bb_ctx* ctx, const char* key, long value);
 int bb_ctx_synchronize(bb_ctx* ctx);
 /* counters for the harness: number of kernels this context has launched */
@@ -111,6 +112,12 @@ int bb_h_poly(bb_ctx* ctx, const void* a, const void* b, const void* c, size_t n
 int bb_bases_upload(bb_ctx* ctx, int group, const void* affine, size_t n, size_t global_offset,
                     size_t global_len, bb_bases** out);
 void bb_bases_free(bb_bases* b);
+/* Builds the table of window multiples 2^(c w) P_i of a resident base vector (c chosen from its
+ * length).  MSMs over these bases then accumulate every window into one bucket set: one summation
+ * by parts and no Horner fold instead of one per window (multiexp.rs:271-300), at (windows x) the
+ * base storage.  Results are unchanged.  With bb_ctx_set_option(ctx, "msm_precompute", 1) the table
+ * is built on first use instead. */
+int bb_bases_precompute(bb_ctx* ctx, bb_bases* bases);
 
 /* ---- MSM: multiexp() (src/multiexp.rs:305-332) ---------------------------------------- */
 /* Sum over i with density bit set of scalars[i] * bases[base_offset + rank(i)], where rank(i)

@@ -1,0 +1,67 @@
+"""MSMs over resident window multiples (bb_bases_precompute / option msm_precompute) in the host-thread
+emulation of the product sources (see test_emulated_pipeline.py): same points, same proofs, same
+error semantics as the per-window path."""
+import numpy as np
+import pytest
+
+import bellman_b200 as bb
+from oracle import o1
+
+import test_gpu_parity as G
+import test_emulated_pipeline as E
+from test_emulated_pipeline import worker                       # noqa: F401  (the emulated-library fixture)
+
+
+@pytest.fixture()
+def precompute(worker):
+    worker.set_option("msm_precompute", 1)
+    yield worker
+    worker.set_option("msm_precompute", 0)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 33, 1000])
+def test_emulated_precompute_g1(precompute, n):
+    G.test_multiexp_g1_matches_oracle(precompute, n)
+
+
+@pytest.mark.parametrize("n", [3, 40, 300])
+def test_emulated_precompute_g2(precompute, n):
+    G.test_multiexp_g2_matches_oracle(precompute, n)
+
+
+def test_emulated_precompute_variants(precompute):
+    E.test_emulated_multiexp_windows(precompute)
+    E.test_emulated_multiexp_density_fast_paths_and_skew(precompute)
+    G.test_multiexp_error_semantics(precompute)
+    # explicit table construction, then queries of different densities / offsets over the same bases
+    n = 600
+    pts = o1.g1_fixed_mul(o1.fr_random(91, n))
+    bases = bb.Bases(precompute, bb.G1, pts).precompute()
+    rng = np.random.default_rng(9)
+    for off, m in ((0, n), (5, 200), (599, 1)):
+        dens = rng.random(m + 50) < 0.8
+        dens[np.cumsum(dens) > n - off] = False              # never run past the end
+        ex = o1.fr_random(92 + off, m + 50)
+        rc, want = o1.multiexp(1, pts, off, dens.astype(np.uint8), ex)
+        assert rc == 0
+        got = bb.multiexp(precompute, (bases, off), bb.DensityTracker(dens), ex).wait()
+        assert np.array_equal(got, want)
+
+
+def test_emulated_precompute_prove_and_shards(precompute):
+    E.test_emulated_prove_mimc322_and_shards(precompute)
+
+
+@pytest.mark.parametrize("variant", [11, 22, 33, 44, 4, 30])
+def test_emulated_accumulate_variants(worker, variant):
+    """msm_acc_variant = g1 + 10 * g2: 1, 2, 4 = launch-bound variants (4 / 5 / 3 CTAs per SM), 3 = next base prefetched during the addition"""
+    worker.set_option("msm_acc_variant", variant)
+    try:
+        for pre in (0, 1):
+            worker.set_option("msm_precompute", pre)
+            G.test_multiexp_g1_matches_oracle(worker, 1000)
+            G.test_multiexp_g2_matches_oracle(worker, 40)
+            G.test_multiexp_error_semantics(worker)
+    finally:
+        worker.set_option("msm_acc_variant", 0)
+        worker.set_option("msm_precompute", 0)

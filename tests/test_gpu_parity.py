@@ -600,3 +600,35 @@ def test_generate_parameters_matches_oracle(worker):
     circuit(_AssemblyAdapter(asm3))
     with pytest.raises(bb.UnexpectedIdentity):
         GEN.generate_parameters(worker, asm3, alpha, beta, gamma, 0, tau)
+
+# resident window multiples (bb_bases_precompute / msm_precompute): same points, one bucket set
+# --------------------------------------------------------------------------------------------
+@pytest.fixture()
+def precompute(worker):
+    worker.set_option("msm_precompute", 1)
+    yield worker
+    worker.set_option("msm_precompute", 0)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 33, 1000, 1 << 14])
+def test_precompute_multiexp_g1(precompute, n):
+    test_multiexp_g1_matches_oracle(precompute, n)
+
+
+@pytest.mark.parametrize("n", [3, 40, 2000])
+def test_precompute_multiexp_g2(precompute, n):
+    test_multiexp_g2_matches_oracle(precompute, n)
+
+
+def test_precompute_variants(precompute):
+    test_multiexp_window_choice_does_not_change_results(precompute)
+    test_multiexp_density_offset_and_fast_paths(precompute)
+    test_multiexp_skewed_scalars(precompute)
+    test_multiexp_error_semantics(precompute)
+    test_multiexp_naive_property_full_size(precompute)
+
+
+def test_precompute_prove(precompute):
+    test_prove_mimc322_matches_oracle(precompute)
+    test_prove_synthetic_chain_trapdoor(precompute, 8191)
+    test_prove_error_precedence(precompute)
