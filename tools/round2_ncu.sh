@@ -9,8 +9,10 @@ mkdir -p gpurun_out
 BENCH="python bench.py --steps 1 --warmup 1 --no-cpu-baseline $*"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/launches_bench.log 2>&1
 python tools/summarize_launches.py gpurun_out/launches.csv > gpurun_out/launches_summary.txt 2>&1; tail -25 gpurun_out/launches_summary.txt
-for k in k_msm_accumulate k_msm_reduce_level k_msm_digits k_ntt_pass k_msm_level_sums; do
-    timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 8 -c 3 -f -o gpurun_out/ncu_$k $BENCH > gpurun_out/ncu_$k.log 2>&1
+# kernel:launches-per-prove -- skip the warm-up prove, capture every launch of the timed one
+for kc in k_msm_accumulate:8:8 k_msm_reduce_level:40:12 k_msm_digits:16:8 k_ntt_pass:21:9; do
+    k=${kc%%:*}; r=${kc#*:}; skip=${r%%:*}; cnt=${r##*:}
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:^$k\$ -s $skip -c $cnt -f -o gpurun_out/ncu_$k $BENCH > gpurun_out/ncu_$k.log 2>&1
     ncu -i gpurun_out/ncu_$k.ncu-rep --page raw --csv 2>/dev/null | python - "$k" <<'PY'
 import csv, sys
 rows = list(csv.reader(sys.stdin))
