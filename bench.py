@@ -38,8 +38,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="prove", choices=["prove", "msm", "ntt"])
     ap.add_argument("--log-size", type=int, default=None, help="log2 of constraints (prove) / points (msm, ntt)")
-    ap.add_argument("--cpu-sample-log", type=int, default=16, help="log2 constraints of the CPU baseline sample")
+    ap.add_argument("--cpu-sample-log", type=int, default=17, help="log2 constraints of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget-s", type=float, default=1200.0, help="--impl reference: wall-clock bound of the proving loop")
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--precompute", type=int, default=0, help="1 = resident window multiples of every base vector (msm_precompute)")
     ap.add_argument("--acc-variant", type=int, default=0)
@@ -135,9 +136,50 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU legs (oracle): the restated bellman rayon path, all host threads
 # ------------------------------------------------------------------------------------------------
-def cpu_prove_sample(sample_log, steps=1, warmup=0):
+def host_cpu_info():
+    """What this process may actually use: affinity mask, cgroup CPU quota, and the thread count the
+    oracle's pool is sized to (the quota when there is one -- hardware_concurrency() still reports every
+    core of the host on a quota'd lease, and a pool larger than the quota only adds contention)."""
+    import math
+    info = {"os_cpu_count": os.cpu_count()}
+    try:
+        info["affinity"] = len(os.sched_getaffinity(0))
+    except Exception:
+        info["affinity"] = None
+    quota = None
+    try:                                            # cgroup v2
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        info["cgroup_cpu_max"] = f"{q} {per}"
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:                                        # cgroup v1
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            info["cgroup_cpu_max"] = f"{q} {per}"
+            if q > 0:
+                quota = q / per
+        except Exception:
+            info["cgroup_cpu_max"] = None
+    info["cgroup_quota_cpus"] = quota
+    n = info["affinity"] or info["os_cpu_count"] or 1
+    if quota:
+        n = max(1, min(n, int(math.ceil(quota))))
+    info["threads"] = int(os.environ.get("BB_ORACLE_THREADS", n))
+    try:
+        info["loadavg_1m"] = os.getloadavg()[0]
+    except Exception:
+        pass
+    return info
+
+
+def cpu_prove_sample(sample_log, steps=1, warmup=0, budget_s=None):
+    """create_proof of the 2^sample_log MiMC chain on the host through the oracle (restated bellman
+    multicore path).  With a budget the warm-up, then the step count, shrink so that the whole leg
+    stays inside it (projected from the first prove); what actually ran is returned."""
     from oracle import o1
-    o1.set_threads(0)
+    host = host_cpu_info()
+    o1.set_threads(host["threads"])
     cores = o1.num_threads()
     rounds = (1 << (sample_log - 1)) - 1
     mc = o1.Mimc(rounds, seed=7)
@@ -147,38 +189,77 @@ def cpu_prove_sample(sample_log, steps=1, warmup=0):
     t0 = time.perf_counter()
     mc.generate()
     t_gen = time.perf_counter() - t0
-    times = []
-    for i in range(warmup + steps):
+    log(f"oracle CRS for 2^{sample_log} generated in {t_gen:.1f} s ({cores} threads)")
+    times, warm_done, t_begin = [], 0, time.perf_counter()
+    want_warm, want_steps = warmup, steps
+    while warm_done < want_warm or len(times) < want_steps:
         r, s = rng.randrange(FR_MODULUS), rng.randrange(FR_MODULUS)
         t0 = time.perf_counter()
         mc.prove(r, s)
         dt = time.perf_counter() - t0
-        if i >= warmup:
+        if warm_done < want_warm:
+            warm_done += 1
+        else:
             times.append(dt)
+        if budget_s is not None:                    # re-plan from the proves seen so far
+            spent = time.perf_counter() - t_begin
+            per = spent / (warm_done + len(times))
+            left = max(0.0, budget_s - spent)
+            room = int(left / per)
+            need = (want_warm - warm_done) + (want_steps - len(times))
+            if room < need:
+                cut = need - room
+                w_cut = min(cut, want_warm - warm_done)
+                want_warm -= w_cut
+                want_steps = max(1, want_steps - (cut - w_cut))
+        log(f"oracle prove {warm_done + len(times)}: {dt:.2f} s")
     n = mc.num_constraints
-    return dict(n=n, times=times, cores=cores, t_gen=t_gen,
-                sample=f"create_proof of a 2^{sample_log}-constraint MiMC chain (same circuit family as the 2^20 workload; "
-                       f"CPU cost per constraint falls ~15% from 2^{sample_log} to 2^20 as the window c = ceil(ln n) grows), "
-                       f"oracle/oracle1 C++ restatement of bellman's multicore path, {cores} threads")
+    return dict(n=n, times=times, cores=cores, t_gen=t_gen, warmup=warm_done, host=host, shape=dict(
+                    num_aux=mc.num_aux if hasattr(mc, "num_aux") else n - 1),
+                sample=f"create_proof of a 2^{sample_log}-constraint MiMC chain, oracle/oracle1 C++ restatement of bellman's "
+                       f"multicore path (c = ceil(ln n) windows, one task per window, 8 MSMs in flight, split FFT), {cores} threads")
 
 
 def run_reference(args):
+    """The reference arm: the restated bellman CPU prover (oracle-1; the Rust crate cannot be built in
+    this image) on the SAME workload as the GPU arm -- the 2^20-constraint MiMC chain unless
+    --log-size says otherwise -- with the same --steps / --warmup, on the host threads this process
+    may use.  --ref-budget-s bounds the leg: if the box is too slow for K+W proves inside it, the
+    warm-up and then the step count shrink and the line reports what ran."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = cpu_prove_sample(args.cpu_sample_log, steps=args.steps, warmup=min(args.warmup, 1))
+    log_n = args.log_size or 20
+    res = cpu_prove_sample(log_n, steps=args.steps, warmup=args.warmup, budget_s=args.ref_budget_s)
     total = sum(res["times"])
-    value = res["n"] * len(res["times"]) / total
+    nsteps = len(res["times"])
+    value = res["n"] * nsteps / total
+    m = res["n"]
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "constraints/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / len(res["times"]),
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (u64 on CPU)", "data": "synthetic",
-        "config": {"workload": "groth16-prove-2^20-mimc-chain", "sample": res["sample"]},
-        "cpu_baseline": {"value": value, "unit": "constraints/s", "cores": res["cores"], "kind": "port", "sample": res["sample"]},
+        "steps": nsteps, "warmup": res["warmup"], "ms_per_step": 1e3 * total / nsteps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64 limbs (381-bit Fp / 255-bit Fr Montgomery integers)",
+        "data": "synthetic",
+        "config": prove_config(log_n, m, m - 1, args.witness, f"host CPU, {res['cores']} threads (rayon-style pool)"),
+        "cpu_baseline": {"value": value, "unit": "constraints/s", "cores": res["cores"], "kind": "port", "sample": res["sample"],
+                         "host": res["host"], "crs_generation_s": res["t_gen"],
+                         "step_seconds": [round(t, 3) for t in res["times"]]},
         "e2e": {"value": value, "unit": "constraints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if nsteps != args.steps or res["warmup"] != args.warmup:
+        line["config"]["note"] = (f"asked for --steps {args.steps} --warmup {args.warmup}; the {args.ref_budget_s:.0f} s budget of this leg "
+                                  f"allowed {nsteps} + {res['warmup']}")
     emit(line)
+
+
+def prove_config(log_n, constraints, num_aux, witness, parallelism):
+    """`config` of the prove workload: identical keys and values in both arms."""
+    half = (constraints // 2) - 1 + 1
+    return {"workload": f"groth16-prove-2^{log_n}-mimc-chain" + ("-boolean-heavy" if witness == "boolean" else ""),
+            "constraints": constraints, "num_aux": num_aux,
+            "msm_sizes": {"h": constraints - 1, "l": num_aux, "a": num_aux + 1, "b_g1": half, "b_g2": half},
+            "ntts": "7 x 2^%d" % log_n, "parallelism": parallelism}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -298,15 +379,11 @@ def run_prove(args):
         "metric": METRIC, "value": value, "unit": "constraints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt_val / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32 limbs (381-bit Fp / 255-bit Fr Montgomery integers)", "data": "synthetic",
-        "config": {"workload": f"groth16-prove-2^{log_n}-mimc-chain" + ("-boolean-heavy" if args.witness == "boolean" else ""),
-                   "constraints": n_constraints, "num_aux": shape["num_aux"],
-                   "msm_sizes": {"h": shape["m"] - 1, "l": shape["num_aux"], "a": shape["a_aux_total"] + 2, "b_g1": shape["b_aux_total"] + 1,
-                                 "b_g2": shape["b_aux_total"] + 1},
-                   "ntts": "7 x 2^%d" % log_n, "parallelism": f"msm-base-range-shards x{world}, NTT replicated",
-                   "crs": "[k_i]G, pseudorandom k_i, made on device; witness: valid MiMC-chain assignment",
-                   "l2": "working set (CRS 430 MB + witness 128 MB) exceeds the 126 MB L2; no flush needed",
-                   "timing": "host wall clock over K steps bracketed by device synchronize (+barrier), max over ranks; "
-                             "kernel figures by CUDA events on the kernels' own streams"},
+        "config": dict(prove_config(log_n, n_constraints, shape["num_aux"], args.witness, f"msm-base-range-shards x{world}, NTT replicated"),
+                       crs="[k_i]G, pseudorandom k_i, made on device; witness: valid MiMC-chain assignment",
+                       l2="working set (CRS 430 MB + witness 128 MB at 2^20) exceeds the 126 MB L2; no flush needed",
+                       timing="host wall clock over K steps bracketed by device synchronize (+barrier), max over ranks; "
+                              "kernel figures by CUDA events on the kernels' own streams"),
         "e2e": {"value": e2e, "unit": "constraints/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * dt_e2e / args.steps},
         "gpu_launches": int(launches),
@@ -333,7 +410,7 @@ def run_prove(args):
         log("cpu_baseline done")
         cpu_v = res["n"] / res["times"][0]
         line["cpu_baseline"] = {"value": cpu_v, "unit": "constraints/s", "cores": res["cores"], "kind": "port", "sample": res["sample"],
-                                "seconds": res["times"][0]}
+                                "seconds": res["times"][0], "host": res["host"]}
     else:
         line["cpu_baseline"] = None
     if rank == 0:

@@ -27,7 +27,7 @@ def _check_line(out, n_gpus):
 
 def test_reference_arm_single_process():
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
-                          "--cpu-sample-log", "10"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--log-size", "10"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0, res.stderr
     _check_line(res.stdout, 1)
 
@@ -35,7 +35,7 @@ def test_reference_arm_single_process():
 def test_reference_arm_under_torchrun_world2():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2",
-           "--warmup", "1", "--cpu-sample-log", "10"]
+           "--warmup", "1", "--log-size", "10"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0, res.stderr
     _check_line(res.stdout, 2)
