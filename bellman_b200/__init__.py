@@ -585,3 +585,10 @@ def synth_mimc(rounds, seed, pinned=False):
 def synth_scalars_device(worker, seed, n, d_ptr):
     """bench-only: fill a device buffer with n pseudorandom canonical scalars (< 2^254)."""
     _check(load_library().bb_synth_scalars_device(worker._h, C.c_uint64(seed), C.c_size_t(n), d_ptr))
+
+
+def fr_dot_device(worker, d_a, d_b, n):
+    """diagnostic: sum a_i b_i mod r of two device arrays of canonical Fr -> (4,) uint64 canonical"""
+    out = np.zeros(4, np.uint64)
+    _check(load_library().bb_diag_fr_dot(worker._h, d_a, d_b, C.c_size_t(n), _ptr(out)))
+    return out

@@ -10,7 +10,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/bellman_b200.h"
+#include "../../include/bellman_b200_diag.h"
 #include "curve.cuh"
 
 namespace bb {

@@ -58,9 +58,42 @@ __global__ void __launch_bounds__(256) k_synth_scalars(Fr* out, size_t n, uint64
     out[i] = v;
 }
 
+// partial[b] = sum over this CTA's grid-stride share of mont(a_i, b_i) = a_i b_i R^-1 (canonical inputs)
+__global__ void __launch_bounds__(256) k_fr_dot(const Fr* __restrict__ a, const Fr* __restrict__ b, size_t n, Fr* partial) {
+    __shared__ Fr sh[256];
+    Fr acc = Fr::zero();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc = acc + a[i] * b[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] = sh[threadIdx.x] + sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
 }  // namespace
 
 extern "C" {
+
+int bb_diag_fr_dot(bb_ctx* ctx, const void* d_a, const void* d_b, size_t n, void* out_fr) {
+    if (!ctx || !out_fr || (n && (!d_a || !d_b))) return BB_ERR_ARG;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    const unsigned blocks = 1024;
+    DevBuf d_p;
+    BB_TRY(d_p.alloc(ctx, blocks * sizeof(Fr)));
+    k_fr_dot<<<blocks, 256, 0, ctx->main_stream>>>((const Fr*)d_a, (const Fr*)d_b, n, d_p.as<Fr>());
+    ctx->count_launch();
+    BB_CUDA(cudaGetLastError());
+    std::vector<Fr> h(blocks);
+    BB_CUDA(cudaMemcpyAsync(h.data(), d_p.p, blocks * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->main_stream));
+    BB_CUDA(cudaStreamSynchronize(ctx->main_stream));
+    Fr acc = Fr::zero();
+    for (const Fr& v : h) acc = acc + v;
+    acc = acc * fr_r2();                                 // (sum a b R^-1) R^2 R^-1 = sum a b, canonical
+    std::memcpy(out_fr, acc.l, 32);
+    return BB_OK;
+}
 
 // d_out[i] = pseudorandom canonical scalar < 2^254, i < n, resident in HBM (bench inputs)
 int bb_synth_scalars_device(bb_ctx* ctx, uint64_t seed, size_t n, void* d_out) {

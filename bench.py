@@ -489,7 +489,17 @@ def run_msm(args):
                          "frac": (achieved / hbm_peak) if achieved else None, "traffic": None, "peak_source": peak_src,
                          "accumulate_ms": acc_ms / args.steps, "device_ms": tot_ms / args.steps, "algorithmic_bytes_per_pair": 128},
             "result_head": bytes(out[0, :2]).hex()}
+    # multiexp.rs:334-378's property at full size: the bases are [k_i]G with k = synth stream 31, so the
+    # MSM must equal [sum k_i e_i]G -- an Fr inner product on the device and one fixed-base multiplication
+    d_k = worker.device_alloc(n * 32)
+    bb.synth_scalars_device(worker, 31, n, d_k)
+    dot = bb.fr_dot_device(worker, d_k, d_sc, n)
+    worker.device_free(d_k)
+    want = bb.fixed_base_mul(worker, bb.G1, dot.reshape(1, 4), form=bb.FORM_CANONICAL)
+    line["config"]["result_check"] = "msm == [sum k_i e_i]G (device Fr inner product + fixed-base multiplication): " + \
+        ("equal" if np.array_equal(np.asarray(out).reshape(-1), np.asarray(want).reshape(-1)) else "MISMATCH")
     emit(line)
+    assert line["config"]["result_check"].endswith("equal"), "MSM result differs from [sum k_i e_i]G"
     worker.close()
 
 

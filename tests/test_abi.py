@@ -12,9 +12,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_symbols():
+    names = set()
+    for hdr in ("bellman_b200.h", "bellman_b200_diag.h"):
+        text = open(os.path.join(ROOT, "include", hdr)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(bb_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
+
+
+def test_public_header_holds_no_diagnostics():
     text = open(os.path.join(ROOT, "include", "bellman_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(bb_[a-z0-9_]+)\s*\(", text)))
+    assert not re.search(r"\bbb_(selftest|synth|diag)_", text)
 
 
 def test_library_is_built_in_tree():
@@ -33,7 +42,7 @@ def test_every_declared_symbol_is_exported():
 def test_header_is_plain_c():
     """the boundary is a C ABI: the header must compile as C99 (no C++ or torch types)"""
     import subprocess, tempfile
-    src = "#include \"bellman_b200.h\"\nint main(void) { bb_witness w; bb_crs_desc d; (void)w; (void)d; return BB_PARTIALS_BYTES == 960 ? 0 : 1; }\n"
+    src = "#include \"bellman_b200_diag.h\"\nint main(void) { bb_witness w; bb_crs_desc d; (void)w; (void)d; return BB_PARTIALS_BYTES == 960 ? 0 : 1; }\n"
     with tempfile.NamedTemporaryFile("w", suffix=".c", delete=False) as f:
         f.write(src)
     res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),

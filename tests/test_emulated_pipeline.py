@@ -66,6 +66,10 @@ def test_emulated_multiexp_g2(worker, n):
     G.test_multiexp_g2_matches_oracle(worker, n)
 
 
+def test_emulated_fr_dot(worker):
+    G.test_fr_dot_diagnostic(worker)
+
+
 def test_emulated_multiexp_windows(worker):
     n = 700
     bases = o1.g1_fixed_mul(o1.fr_random(41, n))

@@ -182,6 +182,28 @@ def test_ntt_full_size_round_trips(worker):
         worker.device_free(d)
 
 
+def test_ntt_2e24_matches_oracle(worker):
+    """BASELINE.json configs[3] at its full size: the forward transform of 2^24 points equals the
+    oracle's (serial_fft semantics, domain.rs:272-314) element for element, and the inverse returns
+    the input (domain.rs:436-457)."""
+    log_n = 24
+    n = 1 << log_n
+    d = worker.device_alloc(n * 32)
+    try:
+        bb.synth_scalars_device(worker, 41, n, d)           # canonical integers < 2^254: valid Montgomery limbs as well
+        v = np.zeros((n, 4), np.uint64); worker.download(d, v)
+        bb.ntt_device(worker, d, log_n, bb.NTT_FFT)
+        fwd = np.zeros_like(v); worker.download(d, fwd)
+        bb.ntt_device(worker, d, log_n, bb.NTT_IFFT)
+        back = np.zeros_like(v); worker.download(d, back)
+        assert np.array_equal(back, v)
+        o1.set_threads(0)
+        want = o1.fft(v, o1.FFT)
+        assert np.array_equal(fwd, want)
+    finally:
+        worker.device_free(d)
+
+
 def test_domain_methods_compose_like_the_reference(worker):
     """The H block of create_proof written out with the individual EvaluationDomain methods
     (prover.rs:222-240) equals the fused bb_h_poly and the oracle; distribute_powers + fft
@@ -334,6 +356,77 @@ def test_multiexp_naive_property_full_size(worker):
     got = _gpu_multiexp(worker, bb.G1, bases, 0, None, ex)
     tot = sum(a * b for a, b in zip(o1.fr_to_ints(ks), o1.fr_to_ints(ex))) % R
     assert np.array_equal(got, o1.g1_fixed_mul(o1.fr_from_ints([tot])))
+
+
+def test_multiexp_large_windows(worker):
+    """choose_window's top entry (c = 20: D = 2^19 buckets, the 2^24 path) and its neighbours, forced at
+    2^18 points; expected point by multiexp.rs:334-378's property."""
+    n = 1 << 18
+    ks, ex = o1.fr_random(63, n), o1.fr_random(64, n)
+    bases_arr = bb.fixed_base_mul(worker, bb.G1, ks)
+    tot = sum(a * b for a, b in zip(o1.fr_to_ints(ks), o1.fr_to_ints(ex))) % R
+    want = o1.g1_fixed_mul(o1.fr_from_ints([tot]))
+    bases = bb.Bases(worker, bb.G1, bases_arr)
+    try:
+        for c in (18, 19, 20, 21, 22):
+            worker.set_option("msm_window_bits", c)
+            got = bb.multiexp(worker, (bases, 0), bb.FullDensity, ex).wait()
+            assert np.array_equal(got, want), c
+    finally:
+        worker.set_option("msm_window_bits", 0)
+        bases.free()
+
+
+def test_multiexp_g2_2e16_matches_oracle(worker):
+    n = 1 << 16
+    bases = bb.fixed_base_mul(worker, bb.G2, o1.fr_random(3100, n))
+    assert np.array_equal(bases[:16], o1.g2_fixed_mul(o1.fr_random(3100, n)[:16]))
+    ex = o1.fr_random(4100, n)
+    o1.set_threads(0)
+    rc, want = o1.multiexp(2, bases, 0, None, ex)
+    assert rc == 0
+    assert np.array_equal(_gpu_multiexp(worker, bb.G2, bases, 0, None, ex), want)
+
+
+def test_fr_dot_diagnostic(worker):
+    n = 5000
+    a, b = o1.fr_to_canonical(o1.fr_random(71, n)), o1.fr_to_canonical(o1.fr_random(72, n))
+    da, db = worker.device_alloc(a.nbytes), worker.device_alloc(b.nbytes)
+    try:
+        worker.upload(da, a); worker.upload(db, b)
+        got = bb.fr_dot_device(worker, da, db, n)
+        want = sum(x * y for x, y in zip(o1.limbs_to_ints(a), o1.limbs_to_ints(b))) % R
+        assert o1.limbs_to_ints(got.reshape(1, 4))[0] == want
+    finally:
+        worker.device_free(da); worker.device_free(db)
+
+
+@pytest.mark.parametrize("log_n,c", [(22, 0), (22, 20)])
+def test_multiexp_synthetic_bases_naive_property(worker, log_n, c):
+    """What bench.py --workload msm asserts at 2^24, here at 2^22: device-made bases [k_i]G, device-made
+    scalars, MSM == [sum k_i e_i]G.  The k_i stream and the fixed-base multiplication are themselves
+    checked against the oracle on a prefix."""
+    n = 1 << log_n
+    bases = bb.Bases.synthetic(worker, bb.G1, 31, n)
+    d_k, d_e = worker.device_alloc(n * 32), worker.device_alloc(n * 32)
+    try:
+        bb.synth_scalars_device(worker, 31, n, d_k)
+        bb.synth_scalars_device(worker, 32, n, d_e)
+        worker.set_option("msm_window_bits", c)
+        got = bb.multiexp_device(worker, (bases, 0), d_e, n, bb.FORM_CANONICAL).wait()
+        dot = bb.fr_dot_device(worker, d_k, d_e, n)
+        want = o1.g1_fixed_mul(o1.fr_from_ints(o1.limbs_to_ints(dot.reshape(1, 4))))
+        assert np.array_equal(np.asarray(got).reshape(-1), want.reshape(-1))
+        # independent of the device dot product: a 4096-term prefix against python integers
+        m = 4096
+        kk = np.zeros((m, 4), np.uint64); ee = np.zeros((m, 4), np.uint64)
+        worker.download(d_k, kk); worker.download(d_e, ee)
+        dm = bb.fr_dot_device(worker, d_k, d_e, m)
+        assert o1.limbs_to_ints(dm.reshape(1, 4))[0] == sum(x * y for x, y in zip(o1.limbs_to_ints(kk), o1.limbs_to_ints(ee))) % R
+    finally:
+        worker.set_option("msm_window_bits", 0)
+        worker.device_free(d_k); worker.device_free(d_e)
+        bases.free()
 
 
 def test_multiexp_error_semantics(worker):
