@@ -172,6 +172,29 @@ int fixed_base_mul(bb_ctx* ctx, FixedTable<F>& tab, const Affine<F>& gen, const 
 }
 
 
+// ---- curve and subgroup membership of a vector of affine points -----------------------------------
+// What G1Affine/G2Affine::from_uncompressed (bls12_381 crate; called by Parameters::read with
+// checked = true and always by VerifyingKey::read, groth16/src/lib.rs:158-183,289-330) verifies
+// beyond the encoding: y^2 = x^3 + b and [r]P = identity.  One thread per point; the first offending
+// index is reported through atomicMin (bad[0]: off the curve, bad[1]: outside the subgroup).  The
+// identity itself passes here: the callers decide where it is allowed.
+BB_HD Fp curve_b(const Fp*) { Fp four = Fp::zero(); four.l[0] = 4; return fp_from_canonical(four); }              // y^2 = x^3 + 4
+BB_HD Fp2 curve_b(const Fp2*) { Fp f = curve_b((const Fp*)nullptr); return {f, f}; }                               // y^2 = x^3 + 4(u + 1)
+
+template <class F>
+__global__ void __launch_bounds__(128) k_points_validate(const Affine<F>* __restrict__ pts, size_t n, int check_subgroup, uint32_t* bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> p = pts[i];
+    if (p.is_identity()) return;
+    F lhs = p.y.sqr(), rhs = p.x.sqr() * p.x + curve_b((const F*)nullptr);
+    if (lhs != rhs) { atomicMin(&bad[0], (uint32_t)i); return; }
+    if (!check_subgroup) return;
+    const uint32_t r[8] = {BBC_FR_MOD_LIST};
+    XYZZ<F> q = XYZZ<F>::from_affine(p).mul_bits(r);
+    if (!q.is_identity()) atomicMin(&bad[1], (uint32_t)i);
+}
+
 // ---- diagnostics: element-wise field / point operations on the device ------------------------
 template <class FE>
 __global__ void k_selftest_field(const FE* a, const FE* b, FE* o, size_t n, int op) {
@@ -489,6 +512,33 @@ int bb_fp_convert(void* fp_inout, size_t n, int to_montgomery) {
         }
         std::memcpy(v + i, &x, sizeof x);
     }
+    return BB_OK;
+}
+// Checks n affine points (ABI format, host memory) the way from_uncompressed does after decoding:
+// on the curve, and (check_subgroup != 0) in the prime-order subgroup.  *first_bad = index of the
+// first offending point (SIZE_MAX if none), *why = 1 off the curve, 2 outside the subgroup.
+int bb_points_validate(bb_ctx* ctx, int group, const void* affine, size_t n, int check_subgroup, size_t* first_bad, int* why) {
+    if (!ctx || (n && !affine) || !first_bad || !why || (group != BB_G1 && group != BB_G2)) { set_error("bb_points_validate: bad argument"); return BB_ERR_ARG; }
+    if (n >= (1ull << 32)) { set_error("bb_points_validate: more than 2^32 points"); return BB_ERR_ARG; }
+    BB_CUDA(cudaSetDevice(ctx->device));
+    *first_bad = (size_t)-1; *why = 0;
+    if (!n) return BB_OK;
+    const size_t stride = group == BB_G1 ? sizeof(G1Affine) : sizeof(G2Affine);
+    DevBuf d_p, d_bad;
+    BB_TRY(d_p.alloc(ctx, n * stride));
+    BB_TRY(d_bad.alloc(ctx, 8));
+    cudaStream_t st = ctx->main_stream;
+    BB_CUDA(cudaMemcpyAsync(d_p.p, affine, n * stride, cudaMemcpyHostToDevice, st));
+    BB_CUDA(cudaMemsetAsync(d_bad.p, 0xff, 8, st));
+    if (group == BB_G1) k_points_validate<Fp><<<cdiv(n, 128), 128, 0, st>>>(d_p.as<G1Affine>(), n, check_subgroup, d_bad.as<uint32_t>());
+    else k_points_validate<Fp2><<<cdiv(n, 128), 128, 0, st>>>(d_p.as<G2Affine>(), n, check_subgroup, d_bad.as<uint32_t>());
+    ctx->count_launch();
+    BB_CUDA(cudaGetLastError());
+    uint32_t bad[2] = {0xffffffffu, 0xffffffffu};
+    BB_CUDA(cudaMemcpyAsync(bad, d_bad.p, 8, cudaMemcpyDeviceToHost, st));
+    BB_CUDA(cudaStreamSynchronize(st));
+    if (bad[0] != 0xffffffffu && bad[0] <= bad[1]) { *first_bad = bad[0]; *why = 1; }
+    else if (bad[1] != 0xffffffffu) { *first_bad = bad[1]; *why = 2; }
     return BB_OK;
 }
 int bb_fixed_base_mul(bb_ctx* ctx, int group, const void* scalars, size_t n, int form, void* out) {

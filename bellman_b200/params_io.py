@@ -7,10 +7,19 @@ u32-length-prefixed h, l, a, b_g1 (G1) and b_g2 (G2).  Points use the uncompress
 x.c1 | x.c0 | y.c1 | y.c0; byte 0 carries the flags (bit 7 compressed = 0, bit 6 infinity).
 
 `read_parameters` returns the arrays `bellman_b200.Parameters` uploads (Montgomery little-endian
-limbs, identity = all-zero).  `checked=True` applies Parameters::read's rules that need no curve
-arithmetic here: flags, canonical coordinates and "no point at infinity" for the vectors and the
-vk (lib.rs:294-330); on-curve and subgroup membership are the loader's caller's business exactly
-when the reference is called with checked=false.
+limbs, identity = all-zero) and applies the reference's acceptance rules:
+
+* encoding (both modes; what `from_uncompressed_unchecked` of the bls12_381 crate rejects): the
+  compression and sort flags must be clear, coordinates must be canonical (< p), and an infinity
+  flag requires every other bit of the encoding to be zero;
+* the point at infinity is rejected in h, l, a, b_g1, b_g2 and ic in BOTH modes (lib.rs:199-207,
+  303-315,337-345) and accepted for alpha, beta, gamma, delta (so that the prover can report the
+  subversion CRS itself, prover.rs:320-324);
+* curve equation and subgroup membership (`from_uncompressed`): always for the VerifyingKey
+  (lib.rs:158-183 has no unchecked mode), for the five vectors when `checked=True`
+  (lib.rs:294-298,328-332).  This is curve arithmetic, so it runs on the device
+  (`bb_points_validate`): pass the `Worker` to use, or one is created on device 0 -- without a CUDA
+  device the call fails, there is no CPU fallback.
 """
 import ctypes as C
 import struct
@@ -47,24 +56,41 @@ def _abi_to_coords(limbs, ncoord, g2):
     return be
 
 
-def _read_points(buf, off, count, g2, checked, what):
+class InvalidData(ValueError):
+    """io::ErrorKind::InvalidData of Parameters::read / VerifyingKey::read"""
+
+
+def _read_points(buf, off, count, g2, what, allow_infinity, validate):
+    """validate: None, or a callable (group_is_g2, points, what) applying the curve checks"""
     size = 192 if g2 else 96
+    name = "G2" if g2 else "G1"
     end = off + count * size
     if end > len(buf):
         raise EOFError(f"{what}: file ends inside the vector")
     raw = np.frombuffer(buf, dtype=np.uint8, count=count * size, offset=off).reshape(count, size)
+    inf = np.zeros(count, bool)
     if count:
         flags = raw[:, 0]
         if (flags & 0x80).any():
-            raise ValueError(f"{what}: compressed point in an uncompressed vector")
-        inf = (flags & 0x40) != 0
-        if checked and inf.any():
-            raise ValueError(f"{what}: point at infinity")            # lib.rs:307-315
+            raise InvalidData(f"invalid {name}: {what} holds a compressed encoding")
         if (flags & 0x20).any():
-            raise ValueError(f"{what}: sort flag set on an uncompressed point")
-    out = _coords_to_abi(raw, 4 if g2 else 2, g2)
+            raise InvalidData(f"invalid {name}: {what} has the sort flag set on an uncompressed point")
+        inf = (flags & 0x40) != 0
+        if inf.any():
+            rest = raw[inf].copy()
+            rest[:, 0] &= 0x3F & ~0x40
+            if rest.any():
+                raise InvalidData(f"invalid {name}: {what} has an infinity flag with non-zero coordinates")
+            if not allow_infinity:
+                raise InvalidData(f"point at infinity in {what}")                 # lib.rs:199-207,303-315
+    try:
+        out = _coords_to_abi(raw, 4 if g2 else 2, g2)                              # rejects coordinates >= p
+    except Exception as e:
+        raise InvalidData(f"invalid {name}: {what}: {e}") from None
     if count:
         out[inf] = 0
+    if validate is not None and count:
+        validate(g2, out, what)
     return out, end
 
 
@@ -74,30 +100,64 @@ def _read_u32(buf, off):
     return struct.unpack_from(">I", buf, off)[0], off + 4
 
 
-def read_verifying_key(buf, off=0, checked=True):
-    vk = {}
-    g1 = lambda o, w: _read_points(buf, o, 1, False, checked, w)
-    g2 = lambda o, w: _read_points(buf, o, 1, True, checked, w)
-    vk["alpha_g1"], off = g1(off, "alpha_g1")
-    vk["beta_g1"], off = g1(off, "beta_g1")
-    vk["beta_g2"], off = g2(off, "beta_g2")
-    vk["gamma_g2"], off = g2(off, "gamma_g2")
-    vk["delta_g1"], off = g1(off, "delta_g1")
-    vk["delta_g2"], off = g2(off, "delta_g2")
-    n, off = _read_u32(buf, off)
-    vk["ic"], off = _read_points(buf, off, n, False, checked, "ic")
+class _Validator:
+    """curve + subgroup checks on the device, with a Worker made on demand"""
+
+    def __init__(self, worker):
+        self.worker, self.own = worker, None
+
+    def __call__(self, g2, points, what):
+        if self.worker is None:
+            from . import Worker
+            self.own = self.worker = Worker(0)
+        first, why = C.c_size_t(), C.c_int()
+        pts = np.ascontiguousarray(points, dtype=np.uint64)
+        _check(load_library().bb_points_validate(self.worker._h, C.c_int(2 if g2 else 1), pts.ctypes.data_as(C.c_void_p),
+                                                 C.c_size_t(pts.shape[0]), C.c_int(1), C.byref(first), C.byref(why)))
+        if why.value:
+            reason = "not on the curve" if why.value == 1 else "not in the prime-order subgroup"
+            raise InvalidData(f"invalid {'G2' if g2 else 'G1'}: {what}[{first.value}] is {reason}")
+
+    def close(self):
+        if self.own is not None:
+            self.own.close()
+
+
+def read_verifying_key(buf, off=0, worker=None, _validator=None):
+    """VerifyingKey::read (lib.rs:158-218): always curve- and subgroup-checked."""
+    val = _validator or _Validator(worker)
+    try:
+        vk = {}
+        g1 = lambda o, w: _read_points(buf, o, 1, False, w, True, val)
+        g2 = lambda o, w: _read_points(buf, o, 1, True, w, True, val)
+        vk["alpha_g1"], off = g1(off, "alpha_g1")
+        vk["beta_g1"], off = g1(off, "beta_g1")
+        vk["beta_g2"], off = g2(off, "beta_g2")
+        vk["gamma_g2"], off = g2(off, "gamma_g2")
+        vk["delta_g1"], off = g1(off, "delta_g1")
+        vk["delta_g2"], off = g2(off, "delta_g2")
+        n, off = _read_u32(buf, off)
+        vk["ic"], off = _read_points(buf, off, n, False, "ic", False, val)
+    finally:
+        if _validator is None:
+            val.close()
     return vk, off
 
 
-def read_parameters(data, checked=True):
-    """bytes of Parameters::write -> dict for bellman_b200.Parameters (+ 'gamma_g2', 'ic')."""
+def read_parameters(data, checked=True, worker=None):
+    """bytes of Parameters::write -> dict for bellman_b200.Parameters (+ 'gamma_g2', 'ic');
+    Parameters::read(reader, checked), lib.rs:289-398."""
     buf = memoryview(data)
-    vk, off = read_verifying_key(buf, 0, checked)
-    p = dict(vk_g1=np.concatenate([vk["alpha_g1"], vk["beta_g1"], vk["delta_g1"]]),
-             vk_g2=np.concatenate([vk["beta_g2"], vk["gamma_g2"], vk["delta_g2"]]), ic=vk["ic"])
-    for name, is_g2 in (("h", False), ("l", False), ("a", False), ("b_g1", False), ("b_g2", True)):
-        n, off = _read_u32(buf, off)
-        p[name], off = _read_points(buf, off, n, is_g2, checked, name)
+    val = _Validator(worker)
+    try:
+        vk, off = read_verifying_key(buf, 0, _validator=val)
+        p = dict(vk_g1=np.concatenate([vk["alpha_g1"], vk["beta_g1"], vk["delta_g1"]]),
+                 vk_g2=np.concatenate([vk["beta_g2"], vk["gamma_g2"], vk["delta_g2"]]), ic=vk["ic"])
+        for name, is_g2 in (("h", False), ("l", False), ("a", False), ("b_g1", False), ("b_g2", True)):
+            n, off = _read_u32(buf, off)
+            p[name], off = _read_points(buf, off, n, is_g2, name, False, val if checked else None)
+    finally:
+        val.close()
     return p
 
 

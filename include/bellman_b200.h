@@ -147,6 +147,12 @@ int bb_point_mul(int group, const void* a_affine, const void* fr_scalar, int for
 int bb_point_compress(int group, const void* affine, uint8_t* out);
 /* in-place canonical <-> Montgomery conversion of n Fp coordinates (host; parameter files) */
 int bb_fp_convert(void* fp_inout, size_t n, int to_montgomery);
+/* The checks G1Affine/G2Affine::from_uncompressed applies after decoding -- what Parameters::read does
+ * with checked = true and VerifyingKey::read always (groth16/src/lib.rs:158-183,289-330): every point on
+ * the curve and, with check_subgroup != 0, of order r.  n affine points in the ABI format, host memory;
+ * computed on the device.  *first_bad = index of the first offending point (SIZE_MAX if none), *why = 1
+ * off the curve, 2 outside the subgroup.  The identity passes (callers decide where it is allowed). */
+int bb_points_validate(bb_ctx* ctx, int group, const void* affine, size_t n, int check_subgroup, size_t* first_bad, int* why);
 /* out[i] = [k_i] * generator, computed on the device (fixed-base); used to manufacture
  * synthetic CRS material of benchmark size (generator.rs:271-296,398-415 equivalent). */
 int bb_fixed_base_mul(bb_ctx* ctx, int group, const void* fr_scalars, size_t n, int form, void* out_affine);
