@@ -482,7 +482,7 @@ def test_prove_mimc322_matches_oracle(worker):
     assert len(rp1) == 192 and rp1 != rp2
     # a key that went through Parameters::write / Parameters::read (groth16/src/lib.rs:258-398)
     from bellman_b200 import params_io
-    reloaded = bb.Parameters(worker, params_io.read_parameters(params_io.write_parameters(mc.export_params())))
+    reloaded = bb.Parameters(worker, params_io.read_parameters(params_io.write_parameters(mc.export_params()), worker=worker))
     assert bb.create_proof(asg, reloaded, r, s) == proof
     # "the proof verifies under the reference verifier": Proof::read + verify_proof
     # (groth16/src/lib.rs:47-99, verifier.rs:23-58) over the oracle's pairing
@@ -673,7 +673,7 @@ def test_generate_parameters_matches_oracle(worker):
     # the generated key proves: same bytes as the oracle's prover on the oracle's key
     from bellman_b200 import params_io
     blob = params_io.write_parameters(got)
-    params = bb.Parameters(worker, params_io.read_parameters(blob))
+    params = bb.Parameters(worker, params_io.read_parameters(blob, worker=worker))
     wit = B.synthesize_witness(B.Bls12, circuit)
     r, s = rng.randrange(R), rng.randrange(R)
     proof = B.proof_bytes(B.create_proof(B.Bls12, circuit, want, r, s))
