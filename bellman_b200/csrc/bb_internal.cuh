@@ -46,7 +46,8 @@ struct bb_ctx {
     std::map<void*, size_t> live_blocks;
     std::vector<cudaStream_t> streams;       // round-robin pool for async jobs
     size_t next_stream = 0;
-    cudaStream_t main_stream = nullptr;
+    cudaStream_t main_stream = nullptr;      // high priority: NTTs / the H pipeline
+    cudaStream_t crit_stream = nullptr;      // high priority: the MSM on a proof's critical path (h)
     std::atomic<uint64_t> launches{0};
     std::atomic<uint64_t> h2d_bytes{0}, d2h_bytes{0};   // host<->device traffic of the hot-path calls
     long opt_msm_window_bits = 0;
@@ -58,6 +59,8 @@ struct bb_ctx {
     long opt_msm_reduce_k1 = 16;
     long opt_msm_big_cap = 0;
     long opt_shard_windows = 4;      // multi-GPU: up to this many window shards per base range (1 = base ranges only)
+    long opt_msm_affine_rounds = -1;  // batched-affine halving rounds per MSM: -1 = by size, 0 = none (XYZZ accumulation only)
+    long opt_msm_affine_batch = 16;   // pairs per thread sharing one link of the inversion chain
     long opt_msm_precompute = 0;     // resident window multiples 2^(c w) P of every base vector (msm.cu: bases_build_table)
     struct ProfEntry { double ms = 0; uint64_t launches = 0, units = 0; };
     std::map<std::string, ProfEntry> prof;
@@ -133,7 +136,7 @@ struct MsmResult {
 };
 int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint64_t* density_bits, size_t density_len,
               const void* scalars, bool scalars_on_device, size_t n, int form, cudaEvent_t wait_for, bb_msm_job** out,
-              const char* tag = nullptr);
+              const char* tag = nullptr, bool critical = false);
 int msm_wait_result(bb_msm_job* job, MsmResult* res);
 int bases_build_table(bb_ctx* ctx, bb_bases* bases);
 

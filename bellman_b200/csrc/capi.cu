@@ -258,7 +258,12 @@ int bb_ctx_create(int device, bb_ctx** out) {
     cudaDeviceProp prop;
     BB_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->num_sms = prop.multiProcessorCount;
-    BB_CUDA(cudaStreamCreateWithFlags(&ctx->main_stream, cudaStreamNonBlocking));
+    // The H pipeline (7 NTTs) and the h MSM that waits for it are the critical path of a proof: their
+    // streams outrank the seven witness MSMs, so their CTAs are placed first whenever an SM has room.
+    int prio_lo = 0, prio_hi = 0;
+    BB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    BB_CUDA(cudaStreamCreateWithPriority(&ctx->main_stream, cudaStreamNonBlocking, prio_hi));
+    BB_CUDA(cudaStreamCreateWithPriority(&ctx->crit_stream, cudaStreamNonBlocking, prio_hi));
     for (int i = 0; i < 8; i++) {
         cudaStream_t s;
         BB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -277,6 +282,7 @@ void bb_ctx_destroy(bb_ctx* ctx) {
     for (auto p : ctx->pinned_free) cudaFreeHost(p);
     for (auto s : ctx->streams) cudaStreamDestroy(s);
     if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
+    if (ctx->crit_stream) cudaStreamDestroy(ctx->crit_stream);
     if (ctx->epoch_ev) cudaEventDestroy(ctx->epoch_ev);
     ntt_free_tables(ctx);
     delete ctx;
@@ -292,6 +298,8 @@ int bb_ctx_set_option(bb_ctx* ctx, const char* key, long value) {
     else if (k == "msm_acc_variant") ctx->opt_msm_acc_variant = value;
     else if (k == "msm_big_cap") ctx->opt_msm_big_cap = value;
     else if (k == "msm_precompute") ctx->opt_msm_precompute = value;
+    else if (k == "msm_affine_rounds") ctx->opt_msm_affine_rounds = value;
+    else if (k == "msm_affine_batch") ctx->opt_msm_affine_batch = value;
     else if (k == "shard_windows") { if (value < 1) { set_error("shard_windows >= 1"); return BB_ERR_ARG; } ctx->opt_shard_windows = value; }
     else if (k == "msm_reduce_k1") { if (value < 2 || (value & (value - 1))) { set_error("msm_reduce_k1 must be a power of two >= 2"); return BB_ERR_ARG; } ctx->opt_msm_reduce_k1 = value; }
     else if (k == "msm_reduce_k") { if (value < 2 || (value & (value - 1))) { set_error("msm_reduce_k must be a power of two >= 2"); return BB_ERR_ARG; } ctx->opt_msm_reduce_k = value; }

@@ -13,6 +13,8 @@
 //   4. k_msm_accumulate  one thread per bucket: gather its affine bases from HBM (32 B
 //                     sector aligned, each read once per window) and sum them with XYZZ
 //                     mixed additions;
+//      (large MSMs first halve every bucket R times with batched-affine pairwise additions, 6 instead
+//      of 10 field multiplications per addition: batch_affine.cuh)
 //   5. k_msm_reduce   summation by parts per window, in parallel: every thread owns K
 //                     adjacent buckets (running-sum trick), lifts its partial by its bucket
 //                     offset with a short double-and-add, and the CTA tree-reduces;
@@ -26,47 +28,9 @@
 #include <ctime>
 
 #include "bb_internal.cuh"
+#include "batch_affine.cuh"
 
 namespace bb {
-
-template <class F> struct PointIO;
-template <> struct PointIO<Fp> { static constexpr int VEC = 6; };     // uint4 loads per affine point
-template <> struct PointIO<Fp2> { static constexpr int VEC = 12; };
-
-template <class F>
-__device__ __forceinline__ Affine<F> ld_affine(const Affine<F>* p) {
-    constexpr int V = PointIO<F>::VEC;
-    const uint4* q = reinterpret_cast<const uint4*>(p);
-    Affine<F> r;
-    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
-#pragma unroll
-    for (int i = 0; i < V; i++) {
-        uint4 v = __ldg(q + i);
-        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
-    }
-    return r;
-}
-template <class T>
-__device__ __forceinline__ void st_words(T* dst, const T& v) {
-    constexpr int V = sizeof(T) / 16;
-    uint4* q = reinterpret_cast<uint4*>(dst);
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
-#pragma unroll
-    for (int i = 0; i < V; i++) q[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
-}
-template <class T>
-__device__ __forceinline__ T ld_words(const T* src) {
-    constexpr int V = sizeof(T) / 16;
-    const uint4* q = reinterpret_cast<const uint4*>(src);
-    T r;
-    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
-#pragma unroll
-    for (int i = 0; i < V; i++) {
-        uint4 v = q[i];
-        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
-    }
-    return r;
-}
 
 struct DigitArgs {
     const Fr* scalars;
@@ -84,7 +48,8 @@ struct DigitArgs {
     uint32_t* sorted;               // mode 1
     uint32_t* ones_list;            // base indices with scalar == 1
     uint32_t* ones_count;
-    uint32_t* err;                  // [0] = min scalar index hitting EOF (0xffffffff none)
+    uint32_t* err;                  // [0] = min scalar index hitting EOF (0xffffffff none), [1] identity base hit,
+                                    // [4] scalars that enter the buckets here, [5] bucket entries (digits) -- profile counters
     int mode;
 };
 
@@ -110,6 +75,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(DigitArgs A) {
         atomicMin(&A.err[0], (uint32_t)i);
         return;
     }
+    if (gi < A.shard_lo || gi >= A.shard_lo + A.shard_n) return;     // another device's shard: its scalar is never read here
     const uint4* q = reinterpret_cast<const uint4*>(A.scalars + i);
     uint4 lo = q[0], hi = q[1];
     Fr s;
@@ -117,7 +83,6 @@ __global__ void __launch_bounds__(256) k_msm_digits(DigitArgs A) {
     s.l[4] = hi.x; s.l[5] = hi.y; s.l[6] = hi.z; s.l[7] = hi.w;
     if (A.montgomery) s = fr_to_canonical(s);                        // to_le_bits, :179
     if (s.is_zero()) return;                                         // Exponent::Zero, :245
-    if (gi < A.shard_lo || gi >= A.shard_lo + A.shard_n) return;     // another device's shard
     uint32_t local = (uint32_t)(gi - A.shard_lo);
     uint32_t rest = s.l[1] | s.l[2] | s.l[3] | s.l[4] | s.l[5] | s.l[6] | s.l[7];
     if (rest == 0 && s.l[0] == 1) {                                  // Exponent::One, :246-252
@@ -125,6 +90,10 @@ __global__ void __launch_bounds__(256) k_msm_digits(DigitArgs A) {
         return;
     }
     const uint32_t D = 1u << (A.c - 1);
+    if (A.mode == 0) {                                               // warp-aggregated count of the pairs consumed
+        const unsigned live = __activemask();
+        if ((threadIdx.x & 31u) == (unsigned)(__ffs((int)live) - 1)) atomicAdd(&A.err[4], (uint32_t)__popc(live));
+    }
     uint32_t carry = 0;
     for (uint32_t w = 0; w < A.W; w++) {
         uint32_t raw = extract_bits(s.l, w * A.c, A.c) + carry;
@@ -170,11 +139,18 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
     return res;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t* in, uint32_t* out, size_t n, uint32_t* tile_sums) {
+// counts are rounded up to a multiple of pad_mask + 1 on the fly (segments of the batched-affine rounds)
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t* in, uint32_t* out, size_t n, uint32_t* tile_sums, uint32_t pad_mask, uint32_t* raw_total) {
     size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS], sum = 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = base + k < n ? in[base + k] : 0; sum += v[k]; }
+    for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = base + k < n ? ((in[base + k] + pad_mask) & ~pad_mask) : 0; sum += v[k]; }
+    if (raw_total) {                                                 // profile counter: entries before padding
+        uint32_t raw = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) raw += base + k < n ? in[base + k] : 0;
+        if (raw) atomicAdd(raw_total, raw);
+    }
     uint32_t total, ex = block_exclusive_scan(sum, &total);
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
@@ -192,14 +168,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(uint32_t* tile_sums,
 }
 // out[i] += tile offset; also writes the grand total at out[n] and copies to cursor
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_finish(uint32_t* out, uint32_t* cursor, size_t n, const uint32_t* tile_sums,
-                                                              const uint32_t* in) {
+                                                              const uint32_t* in, uint32_t pad_mask) {
     size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
     uint32_t off = tile_sums[blockIdx.x];
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
         size_t i = base + k;
         if (i < n) {
-            uint32_t cnt = in[i];                 // `in` aliases `cursor`: read before the overwrite
+            uint32_t cnt = (in[i] + pad_mask) & ~pad_mask;   // `in` aliases `cursor`: read before the overwrite
             uint32_t v = out[i] + off;
             out[i] = v;
             cursor[i] = v;
@@ -258,59 +234,30 @@ __global__ void __launch_bounds__(256) k_size_order(const uint32_t* __restrict__
 }
 
 // ---- bucket accumulation ------------------------------------------------------------------
-template <class F>
+// DENSE = false: entries k of the sorted index array select rows of the base table (bit 31 = negate).
+// DENSE = true:  rows k of the dense array the batched-affine rounds left behind (identity = padding).
+template <class F, bool DENSE>
 __device__ __forceinline__ XYZZ<F> accumulate_range(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                     uint32_t start, uint32_t end, uint32_t* err) {
     XYZZ<F> acc = XYZZ<F>::identity();
     for (uint32_t k = start; k < end; k++) {
-        uint32_t v = sorted[k];
-        Affine<F> p = ld_affine(bases + (v & 0x7fffffffu));
-        if (p.is_identity()) { err[1] = 1; continue; }               // Source::next, multiexp.rs:63-65
-        if (v >> 31) p.y = p.y.neg();
-        acc.add_mixed(p);
-    }
-    return acc;
-}
-
-// Same sum, with the next base already in flight while the current addition runs (one thread owns a
-// serial chain of ~3000 dependent instructions per addition; the gather it needs next is
-// otherwise exposed in full at only 4-8 resident warps per SM).
-template <class F>
-__device__ __forceinline__ XYZZ<F> accumulate_range_prefetch(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                                             uint32_t start, uint32_t end, uint32_t* err) {
-    XYZZ<F> acc = XYZZ<F>::identity();
-    if (start >= end) return acc;
-    uint32_t v = sorted[start];
-    Affine<F> p = ld_affine(bases + (v & 0x7fffffffu));
-    for (uint32_t k = start; k < end; k++) {
-        const uint32_t vc = v;
-        Affine<F> cur = p;
-        if (k + 1 < end) {
-            v = sorted[k + 1];
-            p = ld_affine(bases + (v & 0x7fffffffu));
+        if (DENSE) {
+            Affine<F> p = ld_affine(bases + k);
+            if (p.is_identity()) continue;
+            acc.add_mixed(p);
+        } else {
+            uint32_t v = sorted[k];
+            Affine<F> p = ld_affine(bases + (v & 0x7fffffffu));
+            if (p.is_identity()) { err[1] = 1; continue; }           // Source::next, multiexp.rs:63-65
+            if (v >> 31) p.y = p.y.neg();
+            acc.add_mixed(p);
         }
-        if (cur.is_identity()) { err[1] = 1; continue; }             // Source::next, multiexp.rs:63-65
-        if (vc >> 31) cur.y = cur.y.neg();
-        acc.add_mixed(cur);
     }
     return acc;
 }
 
-template <class F>
-__global__ void __launch_bounds__(128) k_msm_accumulate_prefetch(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ offsets,
-                                                                 const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ order,
-                                                                 XYZZ<F>* buckets, size_t nb, uint32_t cap, uint32_t* err) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nb) return;
-    const uint32_t b = order[t];
-    uint32_t start = offsets[b], end = offsets[b + 1];
-    if (end - start > cap) return;
-    XYZZ<F> acc = accumulate_range_prefetch<F>(bases, sorted, start, end, err);
-    st_words(buckets + b, acc);
-}
-
-template <class F, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ offsets,
+template <class F, bool DENSE>
+__global__ void __launch_bounds__(128) k_msm_accumulate(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ offsets,
                                                         const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ order,
                                                         XYZZ<F>* buckets, size_t nb, uint32_t cap, uint32_t* err) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -318,19 +265,25 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const Affine<F>* _
     const uint32_t b = order[t];
     uint32_t start = offsets[b], end = offsets[b + 1];
     if (end - start > cap) return;                                   // cut into tasks, see k_msm_accumulate_tasks
-    XYZZ<F> acc = accumulate_range<F>(bases, sorted, start, end, err);
+    XYZZ<F> acc = accumulate_range<F, DENSE>(bases, sorted, start, end, err);
     st_words(buckets + b, acc);
 }
 
+// bucket b's rows of the dense array after R halvings of its padded segment
+__global__ void __launch_bounds__(256) k_dense_offsets(const uint32_t* __restrict__ offsets, size_t nb1, uint32_t shift, uint32_t* out) {
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nb1) out[b] = offsets[b] >> shift;
+}
+
 // one thread per task of an oversized bucket (grid-stride: the task count lives on the device)
-template <class F>
+template <class F, bool DENSE>
 __global__ void __launch_bounds__(128) k_msm_accumulate_tasks(const Affine<F>* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                               const uint32_t* __restrict__ big, const BigTask* __restrict__ tasks,
                                                               XYZZ<F>* task_sums, uint32_t* err) {
     const uint32_t ntasks = big[0];
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ntasks; t += gridDim.x * blockDim.x) {
         BigTask tk = tasks[t];
-        XYZZ<F> acc = accumulate_range<F>(bases, sorted, tk.begin, tk.end, err);
+        XYZZ<F> acc = accumulate_range<F, DENSE>(bases, sorted, tk.begin, tk.end, err);
         st_words(task_sums + t, acc);
     }
 }
@@ -554,11 +507,12 @@ struct bb_msm_job {
     uint32_t W_local = 0;            // windows this device owns (all of them unless window-sharded)
     uint32_t W_out = 0;              // window sums copied back: W_local, or 1 with precomputed window multiples
     bool precomp = false;
+    uint32_t affine_rounds = 0;      // batched-affine halving rounds before the XYZZ stage
     size_t n = 0;
     int status = BB_OK;              // pre-launch failure, reported at wait()
     const char* tag = nullptr;       // profile mode: name of this job in the prover's timeline
     DigitArgs dargs{};
-    DevBuf d_scalars, d_density, d_rank, d_counts, d_offsets, d_tiles, d_sorted, d_order, d_buckets, d_partials, d_runs, d_levels, d_onesp, d_final, d_ones, d_err, d_big, d_tasks, d_biglist, d_tasksums;
+    DevBuf d_scalars, d_density, d_rank, d_counts, d_offsets, d_tiles, d_sorted, d_order, d_buckets, d_partials, d_runs, d_levels, d_onesp, d_final, d_ones, d_err, d_big, d_tasks, d_biglist, d_tasksums, d_aff0, d_aff1, d_pre, d_tp, d_doffsets;
     std::vector<uint32_t> h_rank;
     void* h_out = nullptr;           // pinned: [W window sums][1 ones sum] then err[4]
     size_t h_out_bytes = 0;
@@ -649,6 +603,44 @@ static bool trace_on() { static int v = -1; if (v < 0) v = getenv("BB_TRACE") ? 
         }                                                                                         \
     } while (0)
 
+// vals[i] <- 1 / vals[i] for n non-zero field elements (batch_affine.cuh); scratch: batch_invert_scratch_elems(n)
+template <class F>
+int batch_invert_device(bb_ctx* ctx, cudaStream_t st, F* vals, size_t n, F* scratch) {
+    struct Lv { F* vals; F* pre; size_t n; };
+    std::vector<Lv> lv;
+    F* p = scratch;
+    lv.push_back({vals, p, n});
+    p += n;
+    for (size_t m = n; m > BINV_FAN;) {
+        m = (m + BINV_FAN - 1) / BINV_FAN;
+        lv.push_back({p, p + m, m});
+        p += 2 * m;
+    }
+    for (size_t l = 0; l + 1 < lv.size(); l++) {
+        k_binv_up<F><<<cdiv(lv[l + 1].n, 128), 128, 0, st>>>(lv[l].vals, lv[l].n, lv[l].pre, lv[l + 1].vals);
+        ctx->count_launch();
+    }
+    k_binv_top<F><<<1, 32, 0, st>>>(lv.back().vals, (uint32_t)lv.back().n);
+    ctx->count_launch();
+    for (size_t l = lv.size() - 1; l-- > 0;) {
+        k_binv_down<F><<<cdiv(lv[l + 1].n, 128), 128, 0, st>>>(lv[l].vals, lv[l].n, lv[l].pre, lv[l + 1].vals);
+        ctx->count_launch();
+    }
+    BB_CUDA(cudaGetLastError());
+    return BB_OK;
+}
+
+// How many batched-affine halving rounds an MSM gets: each round needs its own inversion chain
+// (~0.5 ms of latency), so small jobs and thinly filled buckets keep the plain XYZZ path.
+uint32_t choose_affine_rounds(const bb_ctx* ctx, size_t n, uint64_t entries, size_t NB) {
+    if (ctx->opt_msm_affine_rounds >= 0) return (uint32_t)(ctx->opt_msm_affine_rounds > 8 ? 8 : ctx->opt_msm_affine_rounds);
+    if (n < (1u << 15)) return 0;
+    const uint64_t avg = entries / (NB ? NB : 1);
+    if (avg >= 12) return 3;
+    if (avg >= 6) return 2;
+    return 0;
+}
+
 template <class F>
 int launch_msm(bb_msm_job* job) {
     bb_ctx* ctx = job->ctx;
@@ -656,13 +648,19 @@ int launch_msm(bb_msm_job* job) {
     const uint32_t W = job->W_local, D = job->D;   // everything below works on the owned windows only
     const size_t NB = (size_t)W * D;
     const size_t n = job->n;
+    const uint64_t entries = (uint64_t)n * W;       // upper bound of the bucket entries (one per non-zero digit)
+    const uint32_t R = job->precomp ? 0u : choose_affine_rounds(ctx, n, entries, NB);
+    const uint32_t pad_mask = (1u << R) - 1u;
+    const uint64_t slots = entries + (uint64_t)NB * pad_mask;   // sorted-array capacity with every bucket padded to 2^R
+    if (slots >= (1ull << 32)) { set_error("bb_msm: %zu scalars x %u windows exceed 2^32 bucket entries; split the job", n, W); return BB_ERR_ARG; }
+    job->affine_rounds = R;
     BB_TRY(job->d_counts.alloc(ctx, (NB + 1) * 4));
     BB_TRY(job->d_offsets.alloc(ctx, (NB + 1) * 4));
     size_t ntiles = (NB + SCAN_TILE - 1) / SCAN_TILE;
     BB_TRY(job->d_tiles.alloc(ctx, ntiles * 4));
-    BB_TRY(job->d_sorted.alloc(ctx, (n ? n : 1) * (size_t)W * 4));
+    BB_TRY(job->d_sorted.alloc(ctx, (slots ? slots : 1) * 4));
     BB_TRY(job->d_ones.alloc(ctx, (n + 4) * 4));
-    BB_TRY(job->d_err.alloc(ctx, 16));
+    BB_TRY(job->d_err.alloc(ctx, 32));
     BB_TRY(job->d_buckets.alloc(ctx, NB * sizeof(XYZZ<F>)));
     BB_TRY(job->d_order.alloc(ctx, (NB + SIZE_BINS) * 4));
     const uint32_t ONES_BLOCKS = 64;
@@ -670,8 +668,9 @@ int launch_msm(bb_msm_job* job) {
 
     BB_CUDA(cudaMemsetAsync(job->d_counts.p, 0, (NB + 1) * 4, st));
     BB_CUDA(cudaMemsetAsync(job->d_err.p, 0xff, 4, st));
-    BB_CUDA(cudaMemsetAsync((char*)job->d_err.p + 4, 0, 12, st));
+    BB_CUDA(cudaMemsetAsync((char*)job->d_err.p + 4, 0, 28, st));
     BB_CUDA(cudaMemsetAsync(job->d_ones.p, 0, 4, st));
+    if (R) BB_CUDA(cudaMemsetAsync(job->d_sorted.p, 0xff, slots * 4, st));      // AFF_NULL padding
 
     const bool prof = ctx->opt_profile != 0;
     if (prof) {
@@ -692,10 +691,10 @@ int launch_msm(bb_msm_job* job) {
     }
     BB_STAGE("histogram");
     uint32_t* offsets = job->d_offsets.as<uint32_t>();
-    k_scan_tiles<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(A.counts, offsets, NB, job->d_tiles.as<uint32_t>());
+    k_scan_tiles<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(A.counts, offsets, NB, job->d_tiles.as<uint32_t>(), pad_mask, A.err + 5);
     k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(job->d_tiles.as<uint32_t>(), ntiles);
     // cursors live in the histogram buffer: after this kernel counts[] holds bucket starts
-    k_scan_finish<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(offsets, A.counts, NB, job->d_tiles.as<uint32_t>(), A.counts);
+    k_scan_finish<<<(unsigned)ntiles, SCAN_THREADS, 0, st>>>(offsets, A.counts, NB, job->d_tiles.as<uint32_t>(), A.counts, pad_mask);
     ctx->count_launch(3);
     BB_STAGE("scan");
     if (n) {
@@ -705,21 +704,64 @@ int launch_msm(bb_msm_job* job) {
     }
     BB_STAGE("scatter");
     const Affine<F>* bases = (const Affine<F>*)(job->precomp ? job->bases->d_table : job->bases->d_points);
+    if (prof) BB_CUDA(cudaEventRecord(job->ev[1], st));
+
+    // ---- batched-affine halving rounds: offsets[NB] padded entries -> offsets[NB] >> R dense rows
+    const Affine<F>* dense = nullptr;
+    if (R) {
+        const uint32_t L = ctx->opt_msm_affine_batch >= 1 && ctx->opt_msm_affine_batch <= 1024 ? (uint32_t)ctx->opt_msm_affine_batch : 16u;
+        const size_t max_pairs = (size_t)(slots / 2);
+        BB_TRY(job->d_aff0.alloc(ctx, (max_pairs ? max_pairs : 1) * sizeof(Affine<F>)));
+        if (R > 1) BB_TRY(job->d_aff1.alloc(ctx, (max_pairs / 2 + 1) * sizeof(Affine<F>)));
+        BB_TRY(job->d_pre.alloc(ctx, (max_pairs ? max_pairs : 1) * sizeof(F)));
+        const size_t T0 = (max_pairs + L - 1) / L;
+        BB_TRY(job->d_tp.alloc(ctx, (T0 + batch_invert_scratch_elems(T0) + 1) * sizeof(F)));
+        F* pre = job->d_pre.as<F>();
+        F* tp = job->d_tp.as<F>();
+        const uint32_t* d_entries = offsets + NB;
+        Affine<F>* bufs[2] = {job->d_aff0.as<Affine<F>>(), job->d_aff1.as<Affine<F>>()};
+        for (uint32_t r = 0; r < R; r++) {
+            const size_t pairs = max_pairs >> r;
+            const size_t T = (pairs + L - 1) / L;
+            if (!T) break;
+            Affine<F>* out = bufs[r & 1];
+            if (r == 0) {
+                PairLoader<F, true> ld{bases, A.sorted};
+                k_aff_phase1<F, true><<<cdiv(T, 128), 128, 0, st>>>(ld, d_entries, r + 1, T, L, pre, tp);
+                BB_TRY(batch_invert_device<F>(ctx, st, tp, T, tp + T));
+                k_aff_phase3<F, true><<<cdiv(T, 128), 128, 0, st>>>(ld, d_entries, r + 1, T, L, pre, tp, out, A.err);
+            } else {
+                PairLoader<F, false> ld{bufs[(r - 1) & 1], nullptr};
+                k_aff_phase1<F, false><<<cdiv(T, 128), 128, 0, st>>>(ld, d_entries, r + 1, T, L, pre, tp);
+                BB_TRY(batch_invert_device<F>(ctx, st, tp, T, tp + T));
+                k_aff_phase3<F, false><<<cdiv(T, 128), 128, 0, st>>>(ld, d_entries, r + 1, T, L, pre, tp, out, A.err);
+            }
+            ctx->count_launch(2);
+            dense = out;
+            BB_STAGE("affine round");
+        }
+        // the buckets' rows of the dense array
+        BB_TRY(job->d_doffsets.alloc(ctx, (NB + 1) * 4));
+        k_dense_offsets<<<cdiv(NB + 1, 256), 256, 0, st>>>(offsets, NB + 1, R, job->d_doffsets.as<uint32_t>());
+        ctx->count_launch();
+        offsets = job->d_doffsets.as<uint32_t>();
+    }
+
     XYZZ<F>* buckets = job->d_buckets.as<XYZZ<F>>();
     uint32_t* order = job->d_order.as<uint32_t>();
     uint32_t* size_hist = order + NB;
     // A bucket is oversized above 4x the mean load (at least 64 entries); it is cut into tasks of
     // about the mean load (at least 32 entries, and few enough that <= ~1M tasks can exist), so
     // the serial chain any thread owns stays short and the task sums are merged by a tree.
-    const uint64_t entries = (uint64_t)n * W;
-    const uint64_t avg = (entries + NB - 1) / NB;
+    const uint64_t rows = slots >> R;                 // what the XYZZ stage walks
+    const uint64_t avg = (rows + NB - 1) / NB;
     uint64_t cap64 = 4 * avg < 64 ? 64 : 4 * avg;
     uint64_t len64 = avg < 32 ? 32 : avg;
-    if (len64 < (entries + 1048575) / 1048576) len64 = (entries + 1048575) / 1048576;
+    if (len64 < (rows + 1048575) / 1048576) len64 = (rows + 1048575) / 1048576;
     if (ctx->opt_msm_big_cap > 0) { cap64 = (uint64_t)ctx->opt_msm_big_cap; len64 = cap64; }
     if (cap64 < len64) cap64 = len64;
     const uint32_t cap = (uint32_t)cap64, task_len = (uint32_t)len64;
-    const size_t max_big = (size_t)(entries / cap) + 16, max_tasks = (size_t)(entries / task_len) + max_big + 16;
+    const size_t max_big = (size_t)(rows / cap) + 16, max_tasks = (size_t)(rows / task_len) + max_big + 16;
     BB_TRY(job->d_big.alloc(ctx, 16));
     BB_TRY(job->d_tasks.alloc(ctx, max_tasks * sizeof(BigTask)));
     BB_TRY(job->d_biglist.alloc(ctx, max_big * sizeof(BigBucket)));
@@ -734,19 +776,16 @@ int launch_msm(bb_msm_job* job) {
     BB_STAGE("order");
     const size_t sh_pt = 128 * sizeof(XYZZ<F>);
     if (sh_pt > 48 * 1024) BB_CUDA(cudaFuncSetAttribute(k_msm_merge_big<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_pt));
-    if (prof) BB_CUDA(cudaEventRecord(job->ev[1], st));
-    // msm_acc_variant = g1 + 10 * g2 (a tuning knob for A/B runs; results never depend on it):
-    // 0 default, 1 / 2 / 4 = 4 / 5 / 3 CTAs per SM through launch bounds, 3 = prefetching loop
-    const int acc_variant = job->group == BB_G2 ? (int)(ctx->opt_msm_acc_variant / 10) % 10 : (int)(ctx->opt_msm_acc_variant % 10);
-    if (acc_variant == 1) k_msm_accumulate<F, 4><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
-    else if (acc_variant == 2) k_msm_accumulate<F, 5><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
-    else if (acc_variant == 4) k_msm_accumulate<F, 3><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);   // G1: 160 registers, no spills, 12 warps per SM
-    else if (acc_variant == 3) k_msm_accumulate_prefetch<F><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
-    else k_msm_accumulate<F, 1><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
     {
         unsigned tgrid = (unsigned)((max_tasks + 127) / 128);
         if (tgrid > (unsigned)ctx->num_sms * 4) tgrid = (unsigned)ctx->num_sms * 4;
-        k_msm_accumulate_tasks<F><<<tgrid, 128, 0, st>>>(bases, A.sorted, big, job->d_tasks.as<BigTask>(), job->d_tasksums.as<XYZZ<F>>(), A.err);
+        if (dense) {
+            k_msm_accumulate<F, true><<<cdiv(NB, 128), 128, 0, st>>>(dense, offsets, nullptr, order, buckets, NB, cap, A.err);
+            k_msm_accumulate_tasks<F, true><<<tgrid, 128, 0, st>>>(dense, nullptr, big, job->d_tasks.as<BigTask>(), job->d_tasksums.as<XYZZ<F>>(), A.err);
+        } else {
+            k_msm_accumulate<F, false><<<cdiv(NB, 128), 128, 0, st>>>(bases, offsets, A.sorted, order, buckets, NB, cap, A.err);
+            k_msm_accumulate_tasks<F, false><<<tgrid, 128, 0, st>>>(bases, A.sorted, big, job->d_tasks.as<BigTask>(), job->d_tasksums.as<XYZZ<F>>(), A.err);
+        }
         unsigned mgrid = max_big < 1024 ? (unsigned)max_big : 1024u;
         k_msm_merge_big<F><<<mgrid, 128, sh_pt, st>>>(big, job->d_biglist.as<BigBucket>(), job->d_tasksums.as<XYZZ<F>>(), buckets);
     }
@@ -772,11 +811,11 @@ int launch_msm(bb_msm_job* job) {
     BB_STAGE("reduce");
     BB_CUDA(cudaGetLastError());
     size_t pts = (size_t)(Wr + 1) * sizeof(XYZZ<F>);
-    job->h_out_bytes = pts + 16;
+    job->h_out_bytes = pts + 32;
     BB_TRY(ctx->pinned_acquire(job->h_out_bytes, &job->h_out));
     BB_CUDA(cudaMemcpyAsync(job->h_out, fin, pts, cudaMemcpyDeviceToHost, st));
-    BB_CUDA(cudaMemcpyAsync((char*)job->h_out + pts, job->d_err.p, 16, cudaMemcpyDeviceToHost, st));
-    ctx->d2h_bytes += pts + 16;
+    BB_CUDA(cudaMemcpyAsync((char*)job->h_out + pts, job->d_err.p, 32, cudaMemcpyDeviceToHost, st));
+    ctx->d2h_bytes += pts + 32;
     if (prof) BB_CUDA(cudaEventRecord(job->ev[3], st));
     return BB_OK;
 }
@@ -828,7 +867,7 @@ int bases_build_table(bb_ctx* ctx, bb_bases* b) {
 namespace bb {
 int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint64_t* density_bits, size_t density_len,
               const void* scalars, bool scalars_on_device, size_t n, int form, cudaEvent_t wait_for, bb_msm_job** out,
-              const char* tag) {
+              const char* tag, bool critical) {
     if (!ctx || !bases || !out || (n && !scalars)) { set_error("bb_msm: null argument"); return BB_ERR_ARG; }
     if (n >= (1ull << 31) || bases->n >= (1ull << 31)) { set_error("bb_msm: more than 2^31 terms"); return BB_ERR_ARG; }
     if (form != BB_FORM_CANONICAL && form != BB_FORM_MONTGOMERY) { set_error("bb_msm: bad form"); return BB_ERR_ARG; }
@@ -837,7 +876,7 @@ int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint
     *out = job;
     job->ctx = ctx; job->bases = bases; job->group = bases->group; job->n = n;
     job->tag = tag;
-    job->st = ctx->pick_stream();
+    job->st = critical ? ctx->crit_stream : ctx->pick_stream();
     if (wait_for) BB_CUDA(cudaStreamWaitEvent(job->st, wait_for, 0));
     if (density_bits && density_len != n) {                 // the assert! at multiexp.rs:324-329
         set_error("density map has %zu entries for %zu exponents", density_len, n);
@@ -889,8 +928,11 @@ int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint
         if ((s = job->d_density.alloc(ctx, words * 8)) != BB_OK) return fail(s);
         if ((s = job->d_rank.alloc(ctx, words * 4)) != BB_OK) return fail(s);
         if (words) {
-            cudaMemcpyAsync(job->d_density.p, density_bits, words * 8, cudaMemcpyHostToDevice, job->st);
-            cudaMemcpyAsync(job->d_rank.p, job->h_rank.data(), words * 4, cudaMemcpyHostToDevice, job->st);
+            if (cudaMemcpyAsync(job->d_density.p, density_bits, words * 8, cudaMemcpyHostToDevice, job->st) != cudaSuccess ||
+                cudaMemcpyAsync(job->d_rank.p, job->h_rank.data(), words * 4, cudaMemcpyHostToDevice, job->st) != cudaSuccess) {
+                set_error("density map upload failed");
+                return fail(BB_ERR_CUDA);
+            }
             ctx->h2d_bytes += words * 12;
         }
         A.density = job->d_density.as<uint64_t>();
@@ -976,8 +1018,19 @@ int msm_wait_result(bb_msm_job* job, MsmResult* res) {
         if (status == BB_OK && cudaEventElapsedTime(&acc_ms, job->ev[1], job->ev[2]) == cudaSuccess &&
             cudaEventElapsedTime(&tot_ms, job->ev[0], job->ev[3]) == cudaSuccess) {
             bool g2 = job->group == BB_G2;
-            job->ctx->prof_add(g2 ? "msm_accumulate_g2" : "msm_accumulate_g1", acc_ms, 1, job->n);
-            job->ctx->prof_add(g2 ? "msm_total_g2" : "msm_total_g1", tot_ms, 1, job->n);
+            // units: the (base, scalar) pairs this job consumed -- density-selected, non-zero, not Exponent::One,
+            // in this shard (counted by k_msm_digits); entries = non-zero digits of those scalars
+            const uint32_t* cnt = (const uint32_t*)((const char*)job->h_out + (size_t)(job->W_out + 1) * (g2 ? sizeof(G2X) : sizeof(G1X)));
+            job->ctx->prof_add(g2 ? "msm_accumulate_g2" : "msm_accumulate_g1", acc_ms, 1, cnt[4]);
+            job->ctx->prof_add(g2 ? "msm_total_g2" : "msm_total_g1", tot_ms, 1, cnt[4]);
+            job->ctx->prof_add(g2 ? "msm_entries_g2" : "msm_entries_g1", acc_ms, 1, cnt[5]);
+            // Fp / Fp2 multiplications of the accumulation stage: halving round r adds entries / 2^(r+1) pairs at 6
+            // each (batch_affine.cuh), the XYZZ stage adds what is left at 10 each -- an upper bound, padding rows and
+            // first entries of a bucket cost nothing
+            uint64_t muls = 0, left = cnt[5];
+            for (uint32_t r = 0; r < job->affine_rounds; r++) { muls += 6 * (left / 2); left -= left / 2; }
+            muls += 10 * left;
+            job->ctx->prof_add(g2 ? "msm_fieldmuls_g2" : "msm_fieldmuls_g1", acc_ms, job->affine_rounds, muls);
             if (job->tag && job->ctx->epoch_ev) {            // device timeline of the prover: ms since the prove started
                 static const char* const mark[4] = {"start", "acc_start", "acc_end", "end"};
                 for (int i = 0; i < 4; i++) {

@@ -206,16 +206,27 @@ int prove_partials_impl(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, uin
     DevBuf d_a, d_b, d_c, d_tmp, d_in, d_aux;
     BB_TRY(d_a.alloc(ctx, m * 32)); BB_TRY(d_b.alloc(ctx, m * 32)); BB_TRY(d_c.alloc(ctx, m * 32)); BB_TRY(d_tmp.alloc(ctx, m * 32));
     BB_TRY(d_in.alloc(ctx, w->n_inputs * 32)); BB_TRY(d_aux.alloc(ctx, w->n_aux * 32));
-    // witness MSMs first: they do not depend on the H pipeline (prover.rs starts them after
-    // h, but all eight are in flight before the first wait, :244-318)
+    // all eight MSMs are in flight before the first wait (prover.rs:244-318)
     cudaStream_t up = ctx->pick_stream();
     const cudaMemcpyKind kind = w->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (w->n_inputs) BB_CUDA(cudaMemcpyAsync(d_in.p, w->input_assignment, w->n_inputs * 32, kind, up));
     if (w->n_aux) BB_CUDA(cudaMemcpyAsync(d_aux.p, w->aux_assignment, w->n_aux * 32, kind, up));
     if (!w->on_device) ctx->h2d_bytes += (w->n_inputs + w->n_aux + 3 * n) * 32;
-    cudaEvent_t ev_up, ev_h;
-    BB_CUDA(cudaEventCreateWithFlags(&ev_up, cudaEventDisableTiming));
-    BB_CUDA(cudaEventCreateWithFlags(&ev_h, cudaEventDisableTiming));
+    // every exit below -- error returns included -- first drains the two streams that touch the buffers
+    // above (the DevBufs go back to the cache when this scope ends) and then destroys the events
+    struct Cleanup {
+        cudaStream_t a, b;
+        cudaEvent_t ev_up = nullptr, ev_h = nullptr;
+        ~Cleanup() {
+            cudaStreamSynchronize(a);
+            cudaStreamSynchronize(b);
+            if (ev_up) cudaEventDestroy(ev_up);
+            if (ev_h) cudaEventDestroy(ev_h);
+        }
+    } guard{st, up};
+    BB_CUDA(cudaEventCreateWithFlags(&guard.ev_up, cudaEventDisableTiming));
+    BB_CUDA(cudaEventCreateWithFlags(&guard.ev_h, cudaEventDisableTiming));
+    const cudaEvent_t ev_up = guard.ev_up, ev_h = guard.ev_h;
     BB_CUDA(cudaEventRecord(ev_up, up));
     size_t b_in_total = 0;                            // get_total_density, prover.rs:288-291
     for (size_t j = 0; j < (w->n_inputs + 63) / 64; j++) {
@@ -227,16 +238,10 @@ int prove_partials_impl(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, uin
     int s = BB_OK;
     static const char* const job_tag[8] = {"h", "l", "a_inputs", "a_aux", "b_g1_inputs", "b_g1_aux", "b_g2_inputs", "b_g2_aux"};
     auto start = [&](int slot, const bb_bases* bases, size_t off, const uint64_t* dens, size_t dens_len, const void* d_sc, size_t cnt, cudaEvent_t ev) {
-        if (s == BB_OK) s = msm_start(ctx, bases, off, dens, dens_len, d_sc, true, cnt, BB_FORM_MONTGOMERY, ev, &jobs[slot], job_tag[slot]);
+        if (s == BB_OK) s = msm_start(ctx, bases, off, dens, dens_len, d_sc, true, cnt, BB_FORM_MONTGOMERY, ev, &jobs[slot], job_tag[slot], slot == 0);
     };
-    start(1, crs->l, 0, nullptr, 0, d_aux.p, w->n_aux, ev_up);                                              // :263-268
-    start(2, crs->a, 0, nullptr, 0, d_in.p, w->n_inputs, ev_up);                                            // :275-280
-    start(3, crs->a, w->n_inputs, w->a_aux_density, w->n_aux, d_aux.p, w->n_aux, ev_up);                    // :281-286
-    start(4, crs->b_g1, 0, w->b_input_density, w->n_inputs, d_in.p, w->n_inputs, ev_up);                    // :296-301
-    start(5, crs->b_g1, b_in_total, w->b_aux_density, w->n_aux, d_aux.p, w->n_aux, ev_up);                  // :302-307
-    start(6, crs->b_g2, 0, w->b_input_density, w->n_inputs, d_in.p, w->n_inputs, ev_up);                    // :312-317
-    start(7, crs->b_g2, b_in_total, w->b_aux_density, w->n_aux, d_aux.p, w->n_aux, ev_up);                  // :318
-    // H pipeline (prover.rs:221-240)
+    // H pipeline first (prover.rs:221-240): it and the h MSM behind it are the longest dependency chain of the
+    // proof; both run on high-priority streams, the seven witness MSMs fill the machine around them
     if (s == BB_OK) {
         auto stage = [&](DevBuf& d, const void* src) -> int {
             if (m > n) BB_CUDA(cudaMemsetAsync((char*)d.p + n * 32, 0, (m - n) * 32, st));   // coeffs.resize(m, zero), domain.rs:69
@@ -245,11 +250,16 @@ int prove_partials_impl(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, uin
         };
         if ((s = stage(d_a, w->a)) == BB_OK && (s = stage(d_b, w->b)) == BB_OK && (s = stage(d_c, w->c)) == BB_OK)
             s = h_poly_device(ctx, st, d_a.as<Fr>(), d_b.as<Fr>(), d_c.as<Fr>(), d_tmp.as<Fr>(), log_m);
-        if (s == BB_OK) {
-            cudaEventRecord(ev_h, st);
-            start(0, crs->h, 0, nullptr, 0, d_a.p, m - 1, ev_h);                                            // :238-244
-        }
+        if (s == BB_OK && cudaEventRecord(ev_h, st) != cudaSuccess) { set_error("cudaEventRecord(H pipeline done) failed"); s = BB_ERR_CUDA; }
+        if (s == BB_OK) start(0, crs->h, 0, nullptr, 0, d_a.p, m - 1, ev_h);                                // :238-244
     }
+    start(1, crs->l, 0, nullptr, 0, d_aux.p, w->n_aux, ev_up);                                              // :263-268
+    start(2, crs->a, 0, nullptr, 0, d_in.p, w->n_inputs, ev_up);                                            // :275-280
+    start(3, crs->a, w->n_inputs, w->a_aux_density, w->n_aux, d_aux.p, w->n_aux, ev_up);                    // :281-286
+    start(4, crs->b_g1, 0, w->b_input_density, w->n_inputs, d_in.p, w->n_inputs, ev_up);                    // :296-301
+    start(5, crs->b_g1, b_in_total, w->b_aux_density, w->n_aux, d_aux.p, w->n_aux, ev_up);                  // :302-307
+    start(6, crs->b_g2, 0, w->b_input_density, w->n_inputs, d_in.p, w->n_inputs, ev_up);                    // :312-317
+    start(7, crs->b_g2, b_in_total, w->b_aux_density, w->n_aux, d_aux.p, w->n_aux, ev_up);                  // :318
     if (while_device_runs && *while_device_runs) (*while_device_runs)();
     // wait() x8 (prover.rs:339-354); always drain every started job.  The h MSM was queued last
     // (it follows the H pipeline), so it is waited for last: the host-side window folds of the
@@ -293,10 +303,6 @@ int prove_partials_impl(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, uin
         std::memcpy(partials, a1, 6 * 96);
         std::memcpy(partials + 576, a2, 2 * 192);
     }
-    cudaStreamSynchronize(st);
-    cudaStreamSynchronize(up);
-    cudaEventDestroy(ev_up);
-    cudaEventDestroy(ev_h);
     return s;
 }
 

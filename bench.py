@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--precompute", type=int, default=0, help="1 = resident window multiples of every base vector (msm_precompute)")
     ap.add_argument("--acc-variant", type=int, default=0)
+    ap.add_argument("--affine-rounds", type=int, default=-1, help="batched-affine halving rounds per MSM (-1 = by size, 0 = XYZZ accumulation only)")
+    ap.add_argument("--affine-batch", type=int, default=0, help="pairs per thread in the batched-affine rounds (0 = default)")
     ap.add_argument("--reduce-k", type=int, default=0)
     ap.add_argument("--reduce-k1", type=int, default=0)
     ap.add_argument("--witness", default="uniform", choices=["uniform", "boolean"],
@@ -294,6 +296,9 @@ def run_prove(args):
         worker.set_option("msm_precompute", 1)
     if args.acc_variant:
         worker.set_option("msm_acc_variant", args.acc_variant)
+    worker.set_option("msm_affine_rounds", args.affine_rounds)
+    if args.affine_batch:
+        worker.set_option("msm_affine_batch", args.affine_batch)
     log("synthesising the MiMC-chain witness (CPU, product-side generator)")
     asg, shape = bb.synth_mimc(rounds, seed=20, pinned=True)
     assert shape["num_constraints"] == 1 << log_n == shape["m"]
@@ -368,13 +373,17 @@ def run_prove(args):
     value = n_constraints * args.steps / dt_val
     e2e = n_constraints * args.steps / dt_e2e
     hbm_peak, peak_src = peaks()
-    # dominant kernel: G1 bucket accumulation.  Algorithmic bytes: 128 B per (base, scalar) pair
-    # (SURVEY.md 8d), pairs = scalars handed to the G1 MSMs of the timed steps (all ranks see all
-    # scalars; each accumulates its base range)
-    alg_bytes = 128.0 * acc_units / max(world, 1)
+    # dominant stage: G1 bucket accumulation (the batched-affine halving rounds k_aff_phase1 / k_aff_phase3 plus the
+    # XYZZ kernel k_msm_accumulate), timed per job by CUDA events on the job's own stream.  Algorithmic bytes: 128 B
+    # per (base, scalar) pair CONSUMED -- counted on the device by k_msm_digits: density-selected,
+    # non-zero, in this rank's shard
+    ent_ms, _, ent_units = worker.profile_read("msm_entries_g1")
+    mul_ms, mul_rounds, mul_units = worker.profile_read("msm_fieldmuls_g1")
+    mul2_ms, _, mul2_units = worker.profile_read("msm_fieldmuls_g2")
+    alg_bytes = 128.0 * acc_units
     achieved = alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None
     tr_pair, tr_src = measured_traffic()
-    pairs_per_launch = acc_units / max(world, 1) / acc_launches if acc_launches else 0
+    pairs_per_launch = acc_units / acc_launches if acc_launches else 0
     line = {
         "metric": METRIC, "value": value, "unit": "constraints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt_val / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -388,20 +397,24 @@ def run_prove(args):
                 "ms_per_step": 1e3 * dt_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "timeline": timeline, "roofline": {"bound": "hbm", "kernel": "k_msm_accumulate<Fp> (G1 bucket accumulation)", "achieved": achieved, "peak": hbm_peak,
+        "timeline": timeline, "roofline": {"bound": "hbm", "kernel": "G1 bucket accumulation stage: k_aff_phase1/k_aff_phase3<Fp> halving rounds + k_msm_accumulate<Fp>", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,
                      "traffic": (tr_pair * pairs_per_launch) if tr_pair else None, "traffic_source": tr_src,
                      "algorithmic_bytes_per_launch": 128.0 * pairs_per_launch, "peak_source": peak_src,
                      "launches": int(acc_launches), "avg_launch_ms": acc_ms / acc_launches if acc_launches else None,
                      "algorithmic_bytes_per_pair": 128,
-                     "share_of_step": (acc_ms / max(world, 1)) / (1e3 * dt_val) if dt_val else None,
+                     "share_of_step": acc_ms / (1e3 * dt_val) if dt_val else None,
                      "share_note": "sum of this kernel's launch durations (CUDA events on each job's stream) over the step time; "
                                    "its launches overlap other streams' kernels, so the sum can approach or exceed the step",
                      "note": "integer-ALU bound, not HBM bound (SURVEY.md 8d): see integer_roofline",
+                     "pairs_per_step": acc_units / args.steps, "bucket_entries_per_step": ent_units / args.steps,
                      "integer_roofline": {"bound": "int32 multiplier", "unit": "G Fp-mul/s",
-                                          "achieved": (10.0 * 16 * acc_units / max(world, 1) / (acc_ms * 1e-3) / 1e9) if acc_ms > 0 else None,
+                                          "achieved": (mul_units / (acc_ms * 1e-3) / 1e9) if acc_ms > 0 else None,
+                                          "achieved_g2_in_fp_mul": (3.0 * mul2_units / (acc2_ms * 1e-3) / 1e9) if acc2_ms > 0 else None,
                                           "peak": 31.2, "peak_source": "profiles/ubench_r01.txt: 288 IMAD.WIDE-class products per Fp-mul at ~30/clk/SM",
-                                          "model": "10 Fp-mul per mixed addition x 16 windows per pair (an upper bound: zero digits are skipped)"},
+                                          "model": "field multiplications counted from the device's own entry count: 6 per batched-affine "
+                                                   "addition (entries/2^(r+1) in halving round r), 10 per XYZZ mixed addition of what is left; "
+                                                   "an Fp2 product = 3 Fp products; jobs overlap, so per-job rates share the machine"},
                      "g2_accumulate_ms_per_step": acc2_ms / args.steps, "g1_msm_total_ms_per_step": tot_ms / args.steps},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -455,6 +468,9 @@ def run_msm(args):
         worker.set_option("msm_reduce_k", args.reduce_k)
     if args.precompute:
         worker.set_option("msm_precompute", 1)
+    worker.set_option("msm_affine_rounds", args.affine_rounds)
+    if args.affine_batch:
+        worker.set_option("msm_affine_batch", args.affine_batch)
     log("generating bases and scalars on the device")
     bases = bb.Bases.synthetic(worker, bb.G1, 31, n)
     d_sc = worker.device_alloc(n * 32)

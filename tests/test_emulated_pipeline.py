@@ -66,6 +66,40 @@ def test_emulated_multiexp_g2(worker, n):
     G.test_multiexp_g2_matches_oracle(worker, n)
 
 
+@pytest.mark.parametrize("n,rounds,batch", [(1, 3, 16), (2, 1, 16), (33, 2, 4), (1000, 3, 16), (1000, 1, 1), (3000, 4, 7)])
+def test_emulated_affine_rounds_g1(worker, n, rounds, batch):
+    force = _force_affine(worker)
+    try:
+        G.test_affine_rounds_g1_match_oracle(worker, force, n, rounds, batch)
+    finally:
+        force(-1)
+
+
+@pytest.mark.parametrize("n,rounds", [(3, 2), (40, 3), (300, 3)])
+def test_emulated_affine_rounds_g2(worker, n, rounds):
+    force = _force_affine(worker)
+    try:
+        G.test_affine_rounds_g2_match_oracle(worker, force, n, rounds)
+    finally:
+        force(-1)
+
+
+def test_emulated_affine_rounds_special(worker):
+    force = _force_affine(worker)
+    try:
+        G.test_affine_rounds_special_pairs(worker, force)
+        G.test_affine_rounds_error_semantics(worker, force)
+    finally:
+        force(-1)
+
+
+def _force_affine(worker):
+    def force(rounds, batch=16):
+        worker.set_option("msm_affine_rounds", rounds)
+        worker.set_option("msm_affine_batch", batch)
+    return force
+
+
 def test_emulated_fr_dot(worker):
     G.test_fr_dot_diagnostic(worker)
 

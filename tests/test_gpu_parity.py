@@ -429,6 +429,109 @@ def test_multiexp_synthetic_bases_naive_property(worker, log_n, c):
         bases.free()
 
 
+@pytest.fixture()
+def affine(worker):
+    """forces the batched-affine halving rounds (batch_affine.cuh) at sizes where they are off by default"""
+    def force(rounds, batch=16):
+        worker.set_option("msm_affine_rounds", rounds)
+        worker.set_option("msm_affine_batch", batch)
+    yield force
+    worker.set_option("msm_affine_rounds", -1)
+    worker.set_option("msm_affine_batch", 16)
+
+
+@pytest.mark.parametrize("n,rounds,batch", [(1, 3, 16), (2, 1, 16), (33, 2, 4), (1000, 3, 16), (1000, 1, 1), (3000, 4, 7), (1 << 14, 3, 16)])
+def test_affine_rounds_g1_match_oracle(worker, affine, n, rounds, batch):
+    affine(rounds, batch)
+    ks = o1.fr_random(1000 + n, n)
+    bases = o1.g1_fixed_mul(ks)
+    ex = o1.fr_random(2000 + n, n)
+    if n > 8:
+        ex[3] = 0; ex[5] = o1.fr_from_ints([1])[0]; ex[6] = o1.fr_from_ints([R - 1])[0]; ex[7] = o1.fr_from_ints([2])[0]
+    rc, want = o1.multiexp(1, bases, 0, None, ex)
+    assert rc == 0
+    assert np.array_equal(_gpu_multiexp(worker, bb.G1, bases, 0, None, ex), want)
+
+
+@pytest.mark.parametrize("n,rounds", [(3, 2), (40, 3), (700, 3)])
+def test_affine_rounds_g2_match_oracle(worker, affine, n, rounds):
+    affine(rounds)
+    bases = o1.g2_fixed_mul(o1.fr_random(3000 + n, n))
+    ex = o1.fr_random(4000 + n, n)
+    rc, want = o1.multiexp(2, bases, 0, None, ex)
+    assert rc == 0
+    assert np.array_equal(_gpu_multiexp(worker, bb.G2, bases, 0, None, ex), want)
+
+
+def test_affine_rounds_special_pairs(worker, affine):
+    """Pairs the affine formulas cannot add directly: equal points (doubling through 2y), opposite points
+    (the identity travels on as a null row), identity rows meeting points; plus skewed buckets and every
+    window size, density maps and the Exponent::Zero / One paths."""
+    rng = np.random.default_rng(9)
+    n = 4000
+    bases = o1.g1_fixed_mul(o1.fr_random(91, n))
+    ex = o1.fr_random(92, n)
+    for rounds in (1, 2, 3, 5):
+        affine(rounds, 5)
+        # the same base many times with the same scalar: every pair of a bucket is a doubling, then again
+        rep = np.repeat(bases[:6], 64, axis=0)
+        ex2 = np.repeat(ex[10:12], 192, axis=0)
+        rc, want = o1.multiexp(1, rep, 0, None, ex2)
+        assert rc == 0 and np.array_equal(_gpu_multiexp(worker, bb.G1, rep, 0, None, ex2), want), rounds
+        # k P and (-k) P side by side: cancellation inside the rounds
+        neg = o1.fr_sub(np.zeros((1, 4), np.uint64), ex[10:11])
+        both = np.concatenate([ex[10:11], neg] * 40)
+        pts = np.repeat(bases[:1], 80, axis=0)
+        got = _gpu_multiexp(worker, bb.G1, pts, 0, None, both)
+        assert not got.any(), rounds
+        mixed = np.concatenate([both, ex[20:60]])
+        mpts = np.concatenate([pts, bases[20:60]])
+        rc, want = o1.multiexp(1, mpts, 0, None, mixed)
+        assert rc == 0 and np.array_equal(_gpu_multiexp(worker, bb.G1, mpts, 0, None, mixed), want), rounds
+    affine(3)
+    cases = {
+        "all twos": o1.fr_from_ints([2] * n),
+        "nibbles": o1.fr_from_ints([int(x) for x in rng.integers(0, 16, n)]),
+        "same 255-bit value": np.repeat(o1.fr_random(93, 1), n, axis=0),
+    }
+    for name, e in cases.items():
+        rc, want = o1.multiexp(1, bases, 0, None, e)
+        assert rc == 0 and np.array_equal(_gpu_multiexp(worker, bb.G1, bases, 0, None, e), want), name
+    try:
+        rc, want = o1.multiexp(1, bases, 0, None, ex)
+        for c in (3, 8, 13, 16):
+            worker.set_option("msm_window_bits", c)
+            assert np.array_equal(_gpu_multiexp(worker, bb.G1, bases, 0, None, ex), want), c
+        worker.set_option("msm_big_cap", 3)
+        assert np.array_equal(_gpu_multiexp(worker, bb.G1, bases, 0, None, ex), want)
+    finally:
+        worker.set_option("msm_window_bits", 0)
+        worker.set_option("msm_big_cap", 0)
+    dens = rng.random(n) < 0.5
+    k = int(dens.sum())
+    b2 = o1.g1_fixed_mul(o1.fr_random(94, 7 + k))
+    kind = rng.integers(0, 4, n)
+    e = ex.copy()
+    e[kind == 0] = 0
+    e[kind == 1] = o1.fr_from_ints([1])[0]
+    rc, want = o1.multiexp(1, b2, 7, dens.astype(np.uint8), e)
+    assert rc == 0 and np.array_equal(_gpu_multiexp(worker, bb.G1, b2, 7, dens, e), want)
+
+
+def test_affine_rounds_error_semantics(worker, affine):
+    """an identity base under a non-zero digit is still UnexpectedIdentity when the rounds consume it"""
+    affine(3)
+    n = 500
+    bases = o1.g1_fixed_mul(o1.fr_random(95, n))
+    ex = o1.fr_random(96, n)
+    bad = bases.copy(); bad[77] = 0
+    with pytest.raises(bb.UnexpectedIdentity):
+        _gpu_multiexp(worker, bb.G1, bad, 0, None, ex)
+    ex0 = ex.copy(); ex0[77] = 0                                        # a zero scalar skips its base (multiexp.rs:245)
+    rc, want = o1.multiexp(1, bad, 0, None, ex0)
+    assert rc == 0 and np.array_equal(_gpu_multiexp(worker, bb.G1, bad, 0, None, ex0), want)
+
+
 def test_multiexp_error_semantics(worker):
     """SURVEY.md App. C 2-4 (multiexp.rs:53-86,242-265,324-329)."""
     bases = o1.g1_fixed_mul(o1.fr_from_ints([5, 6, 7]))

@@ -1,28 +1,25 @@
 #!/bin/bash
 # One GPU call that refreshes the evidence under profiles/ for the kernels of the 2^20 prove:
 #   gpurun --timeout 1500 -- 'bash tools/round2_ncu.sh [extra bench flags]'
-# 1. launch list (per-launch durations, cold-cache/serialised: shares only)   -> gpurun_out/launches.csv
-# 2. one `--set full` capture per hot kernel (3 launches after the warm-up)    -> gpurun_out/ncu_<kernel>.ncu-rep
-# Read the reports on the CPU box:  ncu -i gpurun_out/ncu_<kernel>.ncu-rep --page raw --csv | grep -E 'dram__bytes|sm__warps_active|launch__registers'
+# 1. launch list (per-launch durations, cold-cache/serialised: shares only)   -> gpurun_out/launches.csv + summary
+# 2. one `--set full` capture per hot kernel, a few launches of the second prove -> gpurun_out/ncu_<kernel>_raw.csv
+#    (the .ncu-rep is kept only for the kernels listed in KEEP_REP: gpurun copies back at most 64 MiB)
 set -u
 mkdir -p gpurun_out
 BENCH="python bench.py --steps 1 --warmup 1 --no-cpu-baseline $*"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/launches_bench.log 2>&1
-python tools/summarize_launches.py gpurun_out/launches.csv > gpurun_out/launches_summary.txt 2>&1; tail -25 gpurun_out/launches_summary.txt
-# kernel:launches-per-prove -- skip the warm-up prove, capture every launch of the timed one
-for kc in k_msm_accumulate:8:8 k_msm_reduce_level:40:12 k_msm_digits:16:8 k_ntt_pass:21:9; do
+KEEP_REP="k_aff_phase3 k_msm_accumulate"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv $BENCH > gpurun_out/launches_bench.log 2>&1
+python tools/summarize_launches.py gpurun_out/launches.csv > gpurun_out/launches_summary.txt 2>&1; tail -40 gpurun_out/launches_summary.txt
+# kernel:skip:count -- skip the warm-up prove's launches of that kernel, capture a few of the timed one
+for kc in k_aff_phase3:24:4 k_aff_phase1:24:4 k_msm_accumulate:8:4 k_msm_reduce_level:40:6 k_msm_digits:16:4 k_ntt_pass:21:4 k_binv_up:60:3; do
     k=${kc%%:*}; r=${kc#*:}; skip=${r%%:*}; cnt=${r##*:}
-    timeout 900 ncu --set full --clock-control none --import-source on -k regex:^$k\$ -s $skip -c $cnt -f -o gpurun_out/ncu_$k $BENCH > gpurun_out/ncu_$k.log 2>&1
-    ncu -i gpurun_out/ncu_$k.ncu-rep --page raw --csv 2>/dev/null | python - "$k" <<'PY'
-import csv, sys
-rows = list(csv.reader(sys.stdin))
-if len(rows) < 3:
-    print(sys.argv[1], "no capture"); sys.exit(0)
-hdr = rows[0]
-want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "launch__registers_per_thread", "sm__inst_executed_pipe_fma.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
-idx = [hdr.index(w) for w in want if w in hdr]
-for r in rows[2:]:
-    print(" | ".join(f"{hdr[i]}={r[i][:60]}" for i in idx))
-PY
+    timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base function -k regex:"^${k}\$" -s $skip -c $cnt -f -o gpurun_out/ncu_$k $BENCH > gpurun_out/ncu_$k.log 2>&1
+    if [ -f gpurun_out/ncu_$k.ncu-rep ]; then
+        ncu -i gpurun_out/ncu_$k.ncu-rep --page raw --csv > gpurun_out/ncu_${k}_raw.csv 2>/dev/null
+        case " $KEEP_REP " in *" $k "*) ;; *) rm -f gpurun_out/ncu_$k.ncu-rep ;; esac
+        python tools/ncu_digest.py gpurun_out/ncu_${k}_raw.csv
+    else
+        echo "$k: no capture"; tail -3 gpurun_out/ncu_$k.log
+    fi
 done
+du -sh gpurun_out
