@@ -39,6 +39,31 @@ def test_every_declared_symbol_is_exported():
         assert hasattr(lib, name), f"{name} declared in include/bellman_b200.h but not exported"
 
 
+def test_rust_sys_crate_binds_every_public_symbol():
+    """rust/bellman-b200-sys/src/lib.rs (source only: no Rust toolchain here) declares every function of the
+    public header with the same number of parameters."""
+    def params(text, name):
+        m = re.search(r"\b%s\s*\(" % name, text)
+        assert m, name
+        depth, i = 0, m.end() - 1
+        for j in range(i, len(text)):
+            depth += text[j] == "("
+            depth -= text[j] == ")"
+            if depth == 0:
+                inner = text[i + 1:j].strip()
+                break
+        if inner in ("", "void"):
+            return 0
+        return len([x for x in re.sub(r"\[[^\]]*\]", "", inner).split(",") if x.strip()])
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "bellman_b200.h")).read(), flags=re.S)
+    rs = re.sub(r"//[^\n]*", "", open(os.path.join(ROOT, "rust", "bellman-b200-sys", "src", "lib.rs")).read())
+    names = sorted(set(re.findall(r"\b(bb_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 30
+    for name in names:
+        assert re.search(r"pub fn %s\s*\(" % name, rs), f"{name} missing from the -sys crate"
+        assert params(hdr, name) == params(rs[rs.index("pub fn " + name):], name), name
+
+
 def test_header_is_plain_c():
     """the boundary is a C ABI: the header must compile as C99 (no C++ or torch types)"""
     import subprocess, tempfile
