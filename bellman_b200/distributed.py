@@ -5,6 +5,8 @@ import numpy as np
 
 from . import PARTIALS_BYTES
 
+MSG_BYTES = 159          # error text a failing rank shares with the others (960 + 1 + 159 = 1120 bytes per rank)
+
 
 def shard_range(length, index, count):
     """Contiguous range `index` of `count` over `length` items:
@@ -52,7 +54,7 @@ def create_proof_sharded(assignment, params, full_vk_params, r, s, device_ptrs=N
 
     import threading
 
-    from . import BackendError, SynthesisError, _ERRORS, finalize, finalize_static, prove_partials
+    from . import BackendError, _ERRORS, finalize, finalize_static, prove_partials
 
     # rank 0: the scalar multiplications of the finalisation that need no MSM result run on a host
     # thread while the devices compute the partial sums
@@ -69,13 +71,15 @@ def create_proof_sharded(assignment, params, full_vk_params, r, s, device_ptrs=N
     status, blob, msg = 0, bytes(PARTIALS_BYTES), ""
     try:
         blob = prove_partials(assignment, params, device_ptrs)
-    except (SynthesisError, AssertionError, BackendError) as e:
+    except Exception as e:                               # whatever it is, the other ranks must not be left in the all-gather
         msg = str(e)
-        status = next((code for code, cls in _ERRORS.items() if isinstance(e, cls)), 17)
+        status = next((code for code, cls in _ERRORS.items() if isinstance(e, cls)), 17 if isinstance(e, BackendError) else 255)
     world = dist.get_world_size(group)
     backend = dist.get_backend(group)
     device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-    mine = torch.frombuffer(bytearray(blob + bytes([status])), dtype=torch.uint8).to(device)
+    # one collective: partial sums, status and (on failure) the failing rank's own message
+    text = msg.encode("utf-8", "replace")[:MSG_BYTES].ljust(MSG_BYTES, b"\0")
+    mine = torch.frombuffer(bytearray(blob + bytes([status]) + text), dtype=torch.uint8).to(device)
     out = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(out, mine, group=group)
     gathered = [bytes(t.cpu().numpy()) for t in out]
@@ -84,7 +88,8 @@ def create_proof_sharded(assignment, params, full_vk_params, r, s, device_ptrs=N
     for rank, g in enumerate(gathered):
         if g[PARTIALS_BYTES]:
             code = g[PARTIALS_BYTES]
-            raise _ERRORS.get(code, BackendError)(f"rank {rank} failed with bb_status {code}" + (f": {msg}" if msg else ""))
+            what = g[PARTIALS_BYTES + 1:].rstrip(b"\0").decode("utf-8", "replace")
+            raise _ERRORS.get(code, BackendError)(f"rank {rank} failed with status {code}" + (f": {what}" if what else ""))
     if dist.get_rank(group) == 0:
         return finalize(full_vk_params, [g[:PARTIALS_BYTES] for g in gathered], r, s, static=ahead.get("static"))
     return None

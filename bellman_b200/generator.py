@@ -77,7 +77,8 @@ def generate_parameters(worker, assembly, alpha, beta, gamma, delta, tau, g1_sca
     """`assembly`: the KeypairAssembly as `circuit.synthesize` leaves it (ONE already allocated as
     input 0, generator.rs:188-191).  alpha..tau: integers mod r."""
     q = FR_MODULUS
-    asm = assembly
+    import copy
+    asm = copy.deepcopy(assembly)                             # the caller's assembly is left as synthesis made it
     for i in range(asm.num_inputs):                           # x_i * 0 = 0, :195-202
         asm.enforce([(("input", i), 1)], [], [])
     dom = EvaluationDomain.from_coeffs(worker, np.zeros((asm.num_constraints, 4), dtype=np.uint64))   # :205-206

@@ -14,6 +14,7 @@ configs[2] and configs[3].
 The oracle (oracle/) is used only by the cpu_baseline leg and by --impl reference.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -367,8 +368,17 @@ def run_prove(args):
     log(f"value leg done: {1e3 * dt_val / args.steps:.2f} ms/step; timed region: host buffers (e2e)")
     dt_e2e, proof_e2e, _, h2d, d2h = timed(None, args.steps, args.warmup)
     log(f"e2e leg done: {1e3 * dt_e2e / args.steps:.2f} ms/step")
+    proof_single = None
     if rank == 0:
         assert proof_val == proof_e2e and len(proof_val) == 192
+        if world > 1:
+            # the N-GPU proof must be the single-GPU proof: rank 0 proves once more over an unsharded copy of the
+            # same synthetic CRS (outside every timed region) and compares the bytes
+            log("checking the sharded proof against a single-GPU prove of the same CRS and witness")
+            full = bb.Parameters.synthetic(worker, 21, shape, shard_index=0, shard_count=1)
+            proof_single = bb.create_proof(asg, full, r, s, dev)
+            full.free()
+            assert proof_single == proof_val, "sharded proof differs from the single-GPU proof"
     n_constraints = shape["num_constraints"]
     value = n_constraints * args.steps / dt_val
     e2e = n_constraints * args.steps / dt_e2e
@@ -396,6 +406,9 @@ def run_prove(args):
         "e2e": {"value": e2e, "unit": "constraints/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * dt_e2e / args.steps},
         "gpu_launches": int(launches),
+        "proof_sha256": hashlib.sha256(proof_val).hexdigest() if rank == 0 else None,
+        "proof_check": (None if rank else ("sharded proof == single-GPU proof of the same CRS/witness/r/s (192 bytes equal, rank 0)"
+                                           if world > 1 else "value leg == e2e leg (192 bytes equal); parity with the oracle: tests/")),
         "clocks": clocks,
         "timeline": timeline, "roofline": {"bound": "hbm", "kernel": "G1 bucket accumulation stage: k_aff_phase1/k_aff_phase3<Fp> halving rounds + k_msm_accumulate<Fp>", "achieved": achieved, "peak": hbm_peak,
                      "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None,

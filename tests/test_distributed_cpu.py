@@ -52,7 +52,7 @@ WORKER = textwrap.dedent('''
         D.create_proof_sharded(None, None, None, 1, 2)
         raise SystemExit("expected UnexpectedIdentity")
     except bb.UnexpectedIdentity as e:
-        assert "rank 1" in str(e)
+        assert "rank 1" in str(e) and "identity in the CRS shard of rank 1" in str(e)   # the failing rank's own text, on every rank
     dist.destroy_process_group()
     open(os.path.join(os.path.dirname(os.path.abspath(__file__)), f"ok.{rank}"), "w").write("ok")   # one file per rank: stdout of the two ranks can interleave
 ''')
