@@ -53,6 +53,7 @@ struct bb_ctx {
     long opt_msm_window_bits = 0;
     long opt_ntt_tile_log = 11;
     long opt_ntt_col_bits = 3;
+    long opt_ntt_radix8 = 1;          // register radix-8 windows (k_ntt_pass8) where the tile shape allows; 0 = radix-2 sweeps in shared memory
     long opt_profile = 0;
     long opt_msm_acc_variant = 0;
     long opt_msm_reduce_k = 16;

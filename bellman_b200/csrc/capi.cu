@@ -294,6 +294,7 @@ int bb_ctx_set_option(bb_ctx* ctx, const char* key, long value) {
     if (k == "msm_window_bits") ctx->opt_msm_window_bits = value;
     else if (k == "ntt_tile_log") ctx->opt_ntt_tile_log = value;
     else if (k == "ntt_col_bits") ctx->opt_ntt_col_bits = value;
+    else if (k == "ntt_radix8") ctx->opt_ntt_radix8 = value;
     else if (k == "profile") ctx->opt_profile = value;
     else if (k == "msm_acc_variant") ctx->opt_msm_acc_variant = value;
     else if (k == "msm_big_cap") ctx->opt_msm_big_cap = value;

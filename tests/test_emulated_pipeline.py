@@ -48,6 +48,10 @@ def test_emulated_ntt(worker, log_n):
     G.test_ntt_matches_oracle(worker, log_n)
 
 
+def test_emulated_ntt_radix8(worker):
+    G.test_ntt_register_radix8_equals_radix2_sweeps(worker)
+
+
 def test_emulated_ntt_variants(worker):
     G.test_ntt_tile_shapes_do_not_change_results(worker)
     G.test_ntt_padding_and_degree_limit(worker)

@@ -135,6 +135,23 @@ def test_ntt_tile_shapes_do_not_change_results(worker):
         worker.set_option("ntt_col_bits", 3)
 
 
+def test_ntt_register_radix8_equals_radix2_sweeps(worker):
+    """k_ntt_pass8 (three stages per thread in registers) against k_ntt_pass (one stage per sweep of shared
+    memory) and the oracle, all four transforms, sizes whose passes split into 3+3+2, 3+3+1, 3+3, 3+2, 3 stages."""
+    try:
+        for log_n in (3, 5, 8, 10, 11, 12, 14):
+            v = o1.fr_random(300 + log_n, 1 << log_n)
+            for mode, omode in ((bb.NTT_FFT, o1.FFT), (bb.NTT_IFFT, o1.IFFT), (bb.NTT_COSET_FFT, o1.COSET_FFT), (bb.NTT_ICOSET_FFT, o1.ICOSET_FFT)):
+                want = o1.fft(v, omode)
+                for r8 in (1, 0):
+                    worker.set_option("ntt_radix8", r8)
+                    dom = bb.EvaluationDomain.from_coeffs(worker, v)
+                    [dom.fft, dom.ifft, dom.coset_fft, dom.icoset_fft][mode]()
+                    assert np.array_equal(dom.into_coeffs(), want), (log_n, mode, r8)
+    finally:
+        worker.set_option("ntt_radix8", 1)
+
+
 def test_ntt_padding_and_degree_limit(worker):
     # from_coeffs pads to the next power of two (domain.rs:49-69)
     v = o1.fr_random(8, 13)
