@@ -140,5 +140,10 @@ int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint
               const char* tag = nullptr, bool critical = false);
 int msm_wait_result(bb_msm_job* job, MsmResult* res);
 int bases_build_table(bb_ctx* ctx, bb_bases* bases);
+// vals[i] <- 1 / vals[i] for n NON-ZERO field elements in HBM (Montgomery's trick, fan-in 32, one Fermat inversion);
+// scratch: batch_invert_scratch(n) elements
+int batch_invert_fp(bb_ctx* ctx, cudaStream_t st, Fp* vals, size_t n, Fp* scratch);
+int batch_invert_fp2(bb_ctx* ctx, cudaStream_t st, Fp2* vals, size_t n, Fp2* scratch);
+size_t batch_invert_scratch(size_t n);
 
 }  // namespace bb

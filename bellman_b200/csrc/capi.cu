@@ -120,9 +120,11 @@ int build_fixed_table(FixedTable<F>& t, const Affine<F>& gen) {
     return BB_OK;
 }
 
+// [k_i]G through the 32 x 255 table of byte multiples: at most 32 mixed additions per point, result left in
+// XYZZ form; zzz[i] = its ZZZ coordinate (one for the identity) for the shared inversion below
 template <class F>
 __global__ void __launch_bounds__(128) k_fixed_base_mul(const Affine<F>* __restrict__ table, const Fr* scalars, size_t n, int montgomery,
-                                                        Affine<F>* out) {
+                                                        XYZZ<F>* out, F* zzz) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Fr s = scalars[i];
@@ -132,8 +134,23 @@ __global__ void __launch_bounds__(128) k_fixed_base_mul(const Affine<F>* __restr
         uint32_t d = (s.l[w >> 2] >> (8 * (w & 3))) & 0xffu;
         if (d) acc.add_mixed(table[w * 255 + d - 1]);
     }
-    out[i] = acc.to_affine();
+    out[i] = acc;
+    zzz[i] = acc.is_identity() ? FieldOps<F>::one() : acc.ZZZ;
 }
+// batch normalisation (generator.rs:271-296 normalises its batches the same way): zinv[i] = 1 / ZZZ_i
+template <class F>
+__global__ void __launch_bounds__(128) k_xyzz_normalize(const XYZZ<F>* __restrict__ in, const F* __restrict__ zinv, size_t n, Affine<F>* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    XYZZ<F> P = in[i];
+    if (P.is_identity()) { out[i] = Affine<F>::identity(); return; }
+    F zi3 = zinv[i];
+    F zi2 = (zi3 * P.ZZ).sqr();                          // (z^-3 z^2)^2 = z^-2
+    out[i] = {P.X * zi2, P.Y * zi3};
+}
+
+inline int batch_invert_any(bb_ctx* ctx, cudaStream_t st, Fp* v, size_t n, Fp* scratch) { return batch_invert_fp(ctx, st, v, n, scratch); }
+inline int batch_invert_any(bb_ctx* ctx, cudaStream_t st, Fp2* v, size_t n, Fp2* scratch) { return batch_invert_fp2(ctx, st, v, n, scratch); }
 
 template <class F>
 int fixed_base_mul_dev(bb_ctx* ctx, FixedTable<F>& tab, const Affine<F>& gen, const Fr* d_scalars, size_t n, bool montgomery,
@@ -142,30 +159,34 @@ int fixed_base_mul_dev(bb_ctx* ctx, FixedTable<F>& tab, const Affine<F>& gen, co
         std::lock_guard<std::mutex> g(g_tab_mu);
         BB_TRY(build_fixed_table(tab, gen));
     }
-    if (n) {
-        k_fixed_base_mul<F><<<cdiv(n, 128), 128, 0, st>>>(tab.d_table, d_scalars, n, montgomery, d_out);
+    if (!n) return BB_OK;
+    // chunks of at most 2^22 points keep the XYZZ scratch below 1.6 GB
+    const size_t CH = size_t(1) << 22;
+    const size_t ch = n < CH ? n : CH;
+    DevBuf d_x, d_z;
+    BB_TRY(d_x.alloc(ctx, ch * sizeof(XYZZ<F>)));
+    BB_TRY(d_z.alloc(ctx, (ch + batch_invert_scratch(ch)) * sizeof(F)));
+    for (size_t lo = 0; lo < n; lo += ch) {
+        const size_t len = n - lo < ch ? n - lo : ch;
+        k_fixed_base_mul<F><<<cdiv(len, 128), 128, 0, st>>>(tab.d_table, d_scalars + lo, len, montgomery, d_x.as<XYZZ<F>>(), d_z.as<F>());
+        ctx->count_launch();
+        BB_TRY(batch_invert_any(ctx, st, d_z.as<F>(), len, d_z.as<F>() + len));
+        k_xyzz_normalize<F><<<cdiv(len, 128), 128, 0, st>>>(d_x.as<XYZZ<F>>(), d_z.as<F>(), len, d_out + lo);
         ctx->count_launch();
     }
     BB_CUDA(cudaGetLastError());
+    BB_CUDA(cudaStreamSynchronize(st));                   // the scratch buffers go back to the cache on return
     return BB_OK;
 }
 
 template <class F>
 int fixed_base_mul(bb_ctx* ctx, FixedTable<F>& tab, const Affine<F>& gen, const void* scalars, size_t n, int form, void* out) {
-    {
-        std::lock_guard<std::mutex> g(g_tab_mu);
-        BB_TRY(build_fixed_table(tab, gen));
-    }
     DevBuf d_s, d_o;
     BB_TRY(d_s.alloc(ctx, n * 32));
     BB_TRY(d_o.alloc(ctx, n * sizeof(Affine<F>)));
     cudaStream_t st = ctx->main_stream;
     BB_CUDA(cudaMemcpyAsync(d_s.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
-    if (n) {
-        k_fixed_base_mul<F><<<cdiv(n, 128), 128, 0, st>>>(tab.d_table, d_s.as<Fr>(), n, form == BB_FORM_MONTGOMERY, d_o.as<Affine<F>>());
-        ctx->count_launch();
-    }
-    BB_CUDA(cudaGetLastError());
+    BB_TRY(fixed_base_mul_dev<F>(ctx, tab, gen, d_s.as<Fr>(), n, form == BB_FORM_MONTGOMERY, d_o.as<Affine<F>>(), st));
     BB_CUDA(cudaMemcpyAsync(out, d_o.p, n * sizeof(Affine<F>), cudaMemcpyDeviceToHost, st));
     BB_CUDA(cudaStreamSynchronize(st));
     return BB_OK;

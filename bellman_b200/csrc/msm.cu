@@ -849,6 +849,11 @@ int build_table_t(bb_ctx* ctx, bb_bases* b, uint32_t c, uint32_t W, uint32_t slo
 }  // namespace
 
 namespace bb {
+int batch_invert_fp(bb_ctx* ctx, cudaStream_t st, Fp* vals, size_t n, Fp* scratch) { return batch_invert_device<Fp>(ctx, st, vals, n, scratch); }
+int batch_invert_fp2(bb_ctx* ctx, cudaStream_t st, Fp2* vals, size_t n, Fp2* scratch) { return batch_invert_device<Fp2>(ctx, st, vals, n, scratch); }
+size_t batch_invert_scratch(size_t n) { return batch_invert_scratch_elems(n); }
+}  // namespace bb
+namespace bb {
 // Builds the window-multiple table of a base vector for the window size its length selects (the
 // window of an MSM over these bases is then fixed, whatever the density of the query).
 int bases_build_table(bb_ctx* ctx, bb_bases* b) {
