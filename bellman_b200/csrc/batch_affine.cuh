@@ -16,8 +16,9 @@
 //   k_aff_phase1   thread t walks its pairs j = t, t+T, t+2T, ...: denominator d_j (x2-x1, or 2y for a
 //                  doubling, or 1 when the pair needs no inversion), running product, exclusive prefixes
 //                  to HBM; the thread's total goes to tp[t]
-//   batch_invert   tp[t] <- 1/tp[t] for all T threads: the same trick applied recursively with fan-in
-//                  32 until one element is left, ONE Fermat inversion per round, then back down
+//   batch_invert   tp[t] <- 1/tp[t] for all T threads: the same trick once more with fan-in 32, then
+//                  shared-memory product scans over tiles of 256 until one tile is left, ONE Fermat
+//                  inversion per round, then back down
 //   k_aff_phase3   the thread walks its pairs backwards: 1/d_j = run * prefix_j, run *= d_j, and finishes
 //                  the affine addition; result j to the next array.
 // The results are group elements: any evaluation order gives the same bucket sums, hence the same
@@ -102,27 +103,25 @@ __global__ void __launch_bounds__(128) k_binv_down(F* __restrict__ vals, size_t 
     }
     st_words(vals + lo, run);
 }
-// top: at most FAN elements left.  One thread: prefixes, ONE inversion (Fermat), back-substitution.
-template <class F>
-__global__ void __launch_bounds__(32) k_binv_top(F* vals, uint32_t n) {
-    if (blockIdx.x || threadIdx.x) return;
-    F pre[BINV_FAN];
-    F run = ld_words(vals);
-    for (uint32_t i = 1; i < n; i++) { pre[i] = run; run = run * ld_words(vals + i); }
-    run = FieldOps<F>::inv(run);
-    for (uint32_t i = n - 1; i > 0; i--) {
-        F v = ld_words(vals + i);
-        st_words(vals + i, run * pre[i]);
-        run = run * v;
-    }
-    st_words(vals, run);
-}
+// Upper levels: one CTA per tile of SCAN_TILE elements, Hillis-Steele product scans in shared memory
+// (depth 2 log2(tile) multiplications instead of 3 * fan-in for the serial walk -- these levels are tiny, so
+// the extra work is irrelevant and the latency of the chain is what counts: it is paid once per halving round
+// on the job's critical path).  pre[i] / suf[i] = products of the tile's elements before / after i,
+// up[tile] = product of the tile.
+constexpr uint32_t BINV_TILE = 256;
 
-// scratch elements batch_invert needs for n values (prefixes of level 0 + every upper level twice)
+// (the tile-scan kernels k_binv_scan_up / k_binv_scan_down / k_binv_top live in msm.cu next to their launches)
+
+// scratch elements batch_invert needs for n values: prefixes of level 0, then values + prefixes + suffixes of
+// every upper level
 inline size_t batch_invert_scratch_elems(size_t n) {
     size_t tot = n;                       // pre of level 0
-    while (n > BINV_FAN) { n = (n + BINV_FAN - 1) / BINV_FAN; tot += 2 * n; }
-    return tot + 2 * BINV_FAN;
+    if (n > BINV_TILE) {
+        n = (n + BINV_FAN - 1) / BINV_FAN;
+        tot += 3 * n;
+        while (n > BINV_TILE) { n = (n + BINV_TILE - 1) / BINV_TILE; tot += 3 * n; }
+    }
+    return tot + 2 * BINV_TILE;
 }
 
 // ---- one pair -----------------------------------------------------------------------------------------

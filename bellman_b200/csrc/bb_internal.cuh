@@ -47,7 +47,7 @@ struct bb_ctx {
     std::vector<cudaStream_t> streams;       // round-robin pool for async jobs
     size_t next_stream = 0;
     cudaStream_t main_stream = nullptr;      // high priority: NTTs / the H pipeline
-    cudaStream_t crit_stream = nullptr;      // high priority: the MSM on a proof's critical path (h)
+    cudaStream_t crit_stream[2] = {nullptr, nullptr};   // high priority: the MSMs on a proof's critical path (h, and the G2 job)
     std::atomic<uint64_t> launches{0};
     std::atomic<uint64_t> h2d_bytes{0}, d2h_bytes{0};   // host<->device traffic of the hot-path calls
     long opt_msm_window_bits = 0;
@@ -56,8 +56,8 @@ struct bb_ctx {
     long opt_ntt_radix8 = 1;          // register radix-8 windows (k_ntt_pass8) where the tile shape allows; 0 = radix-2 sweeps in shared memory
     long opt_profile = 0;
     long opt_msm_acc_variant = 0;
-    long opt_msm_reduce_k = 16;
-    long opt_msm_reduce_k1 = 16;
+    long opt_msm_reduce_k = 4;       // entries per thread and level of the bucket reduction: 4 halves the length of the
+    long opt_msm_reduce_k1 = 4;      // dependent-addition chain of 16 (2K per level, log_K D levels) for 1.25x its additions
     long opt_msm_big_cap = 0;
     long opt_shard_windows = 4;      // multi-GPU: up to this many window shards per base range (1 = base ranges only)
     long opt_msm_affine_rounds = -1;  // batched-affine halving rounds per MSM: -1 = by size, 0 = none (XYZZ accumulation only)
@@ -137,7 +137,7 @@ struct MsmResult {
 };
 int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint64_t* density_bits, size_t density_len,
               const void* scalars, bool scalars_on_device, size_t n, int form, cudaEvent_t wait_for, bb_msm_job** out,
-              const char* tag = nullptr, bool critical = false);
+              const char* tag = nullptr, int critical = 0);
 int msm_wait_result(bb_msm_job* job, MsmResult* res);
 int bases_build_table(bb_ctx* ctx, bb_bases* bases);
 // vals[i] <- 1 / vals[i] for n NON-ZERO field elements in HBM (Montgomery's trick, fan-in 32, one Fermat inversion);

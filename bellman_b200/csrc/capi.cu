@@ -284,7 +284,7 @@ int bb_ctx_create(int device, bb_ctx** out) {
     int prio_lo = 0, prio_hi = 0;
     BB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     BB_CUDA(cudaStreamCreateWithPriority(&ctx->main_stream, cudaStreamNonBlocking, prio_hi));
-    BB_CUDA(cudaStreamCreateWithPriority(&ctx->crit_stream, cudaStreamNonBlocking, prio_hi));
+    for (auto& cs : ctx->crit_stream) BB_CUDA(cudaStreamCreateWithPriority(&cs, cudaStreamNonBlocking, prio_hi));
     for (int i = 0; i < 8; i++) {
         cudaStream_t s;
         BB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -303,7 +303,7 @@ void bb_ctx_destroy(bb_ctx* ctx) {
     for (auto p : ctx->pinned_free) cudaFreeHost(p);
     for (auto s : ctx->streams) cudaStreamDestroy(s);
     if (ctx->main_stream) cudaStreamDestroy(ctx->main_stream);
-    if (ctx->crit_stream) cudaStreamDestroy(ctx->crit_stream);
+    for (auto& cs : ctx->crit_stream) if (cs) cudaStreamDestroy(cs);
     if (ctx->epoch_ev) cudaEventDestroy(ctx->epoch_ev);
     ntt_free_tables(ctx);
     delete ctx;

@@ -509,6 +509,7 @@ struct bb_msm_job {
     bool precomp = false;
     uint32_t affine_rounds = 0;      // batched-affine halving rounds before the XYZZ stage
     size_t n = 0;
+    size_t n_dense = 0;              // scalars the density map selects (= n for FullDensity): what can reach the buckets
     int status = BB_OK;              // pre-launch failure, reported at wait()
     const char* tag = nullptr;       // profile mode: name of this job in the prover's timeline
     DigitArgs dargs{};
@@ -603,27 +604,112 @@ static bool trace_on() { static int v = -1; if (v < 0) v = getenv("BB_TRACE") ? 
         }                                                                                         \
     } while (0)
 
+// ---- upper levels of the batch inversion (batch_affine.cuh) ------------------------------------------
+template <class F>
+__device__ __forceinline__ void tile_scans(F v, uint32_t cnt, F* sh, F* pre_out, F* suf_out, F* total) {
+    const uint32_t t = threadIdx.x;
+    // inclusive prefix products
+    st_words(sh + t, v);
+    __syncthreads();
+    F acc = v;
+    for (uint32_t d = 1; d < BINV_TILE; d <<= 1) {
+        F other = acc;
+        const bool take = t >= d && t < cnt;
+        if (take) other = ld_words(sh + t - d);
+        __syncthreads();
+        if (take) { acc = other * acc; st_words(sh + t, acc); }
+        __syncthreads();
+    }
+    *total = ld_words(sh + cnt - 1);
+    *pre_out = t == 0 ? FieldOps<F>::one() : ld_words(sh + (t < cnt ? t : cnt) - 1);
+    __syncthreads();
+    // inclusive suffix products
+    st_words(sh + t, v);
+    __syncthreads();
+    acc = v;
+    for (uint32_t d = 1; d < BINV_TILE; d <<= 1) {
+        F other = acc;
+        const bool take = t + d < cnt;
+        if (take) other = ld_words(sh + t + d);
+        __syncthreads();
+        if (take) { acc = acc * other; st_words(sh + t, acc); }
+        __syncthreads();
+    }
+    *suf_out = t + 1 < cnt ? ld_words(sh + t + 1) : FieldOps<F>::one();
+    __syncthreads();
+}
+
+template <class F>
+__global__ void __launch_bounds__(BINV_TILE) k_binv_scan_up(const F* __restrict__ vals, size_t n, F* __restrict__ pre, F* __restrict__ suf,
+                                                            F* __restrict__ up) {
+    extern __shared__ uint4 shraw[];
+    F* sh = reinterpret_cast<F*>(shraw);
+    const size_t base = (size_t)blockIdx.x * BINV_TILE;
+    const uint32_t cnt = n - base < BINV_TILE ? (uint32_t)(n - base) : BINV_TILE;
+    const size_t i = base + threadIdx.x;
+    F v = threadIdx.x < cnt ? ld_words(vals + i) : FieldOps<F>::one();
+    F p, q, tot;
+    tile_scans<F>(v, cnt, sh, &p, &q, &tot);
+    if (threadIdx.x < cnt) { st_words(pre + i, p); st_words(suf + i, q); }
+    if (threadIdx.x == 0) st_words(up + blockIdx.x, tot);
+}
+// up[tile] now holds 1 / (product of the tile): vals[i] <- up * pre[i] * suf[i] = 1 / vals[i]
+template <class F>
+__global__ void __launch_bounds__(BINV_TILE) k_binv_scan_down(F* __restrict__ vals, size_t n, const F* __restrict__ pre, const F* __restrict__ suf,
+                                                              const F* __restrict__ up) {
+    const size_t i = (size_t)blockIdx.x * BINV_TILE + threadIdx.x;
+    if (i >= n) return;
+    st_words(vals + i, ld_words(up + blockIdx.x) * (ld_words(pre + i) * ld_words(suf + i)));
+}
+// top: at most BINV_TILE elements left, one CTA: scans, ONE inversion (Fermat, thread 0), back-substitution
+template <class F>
+__global__ void __launch_bounds__(BINV_TILE) k_binv_top(F* vals, uint32_t n) {
+    extern __shared__ uint4 shraw[];
+    F* sh = reinterpret_cast<F*>(shraw);
+    __shared__ F inv_total;
+    F v = threadIdx.x < n ? ld_words(vals + threadIdx.x) : FieldOps<F>::one();
+    F p, q, tot;
+    tile_scans<F>(v, n, sh, &p, &q, &tot);
+    if (threadIdx.x == 0) inv_total = FieldOps<F>::inv(tot);
+    __syncthreads();
+    if (threadIdx.x < n) st_words(vals + threadIdx.x, inv_total * (p * q));
+}
+
 // vals[i] <- 1 / vals[i] for n non-zero field elements (batch_affine.cuh); scratch: batch_invert_scratch_elems(n)
 template <class F>
 int batch_invert_device(bb_ctx* ctx, cudaStream_t st, F* vals, size_t n, F* scratch) {
-    struct Lv { F* vals; F* pre; size_t n; };
+    if (!n) return BB_OK;
+    const size_t sh = BINV_TILE * sizeof(F);
+    // level 0 -> 1: serial fan-in 32 per thread (work-efficient: this is the big level); above: tile scans
+    struct Lv { F* vals; F* pre; F* suf; size_t n; };
     std::vector<Lv> lv;
     F* p = scratch;
-    lv.push_back({vals, p, n});
+    lv.push_back({vals, p, nullptr, n});
     p += n;
-    for (size_t m = n; m > BINV_FAN;) {
-        m = (m + BINV_FAN - 1) / BINV_FAN;
-        lv.push_back({p, p + m, m});
-        p += 2 * m;
-    }
-    for (size_t l = 0; l + 1 < lv.size(); l++) {
-        k_binv_up<F><<<cdiv(lv[l + 1].n, 128), 128, 0, st>>>(lv[l].vals, lv[l].n, lv[l].pre, lv[l + 1].vals);
+    if (n > BINV_TILE) {
+        size_t m = (n + BINV_FAN - 1) / BINV_FAN;
+        lv.push_back({p, p + m, p + 2 * m, m});
+        p += 3 * m;
+        while (m > BINV_TILE) {
+            m = (m + BINV_TILE - 1) / BINV_TILE;
+            lv.push_back({p, p + m, p + 2 * m, m});
+            p += 3 * m;
+        }
+        k_binv_up<F><<<cdiv(lv[1].n, 128), 128, 0, st>>>(lv[0].vals, lv[0].n, lv[0].pre, lv[1].vals);
         ctx->count_launch();
+        for (size_t l = 1; l + 1 < lv.size(); l++) {
+            k_binv_scan_up<F><<<(unsigned)lv[l + 1].n, BINV_TILE, sh, st>>>(lv[l].vals, lv[l].n, lv[l].pre, lv[l].suf, lv[l + 1].vals);
+            ctx->count_launch();
+        }
     }
-    k_binv_top<F><<<1, 32, 0, st>>>(lv.back().vals, (uint32_t)lv.back().n);
+    k_binv_top<F><<<1, BINV_TILE, sh, st>>>(lv.back().vals, (uint32_t)lv.back().n);
     ctx->count_launch();
-    for (size_t l = lv.size() - 1; l-- > 0;) {
-        k_binv_down<F><<<cdiv(lv[l + 1].n, 128), 128, 0, st>>>(lv[l].vals, lv[l].n, lv[l].pre, lv[l + 1].vals);
+    if (lv.size() > 1) {
+        for (size_t l = lv.size() - 2; l >= 1; l--) {
+            k_binv_scan_down<F><<<(unsigned)lv[l + 1].n, BINV_TILE, 0, st>>>(lv[l].vals, lv[l].n, lv[l].pre, lv[l].suf, lv[l + 1].vals);
+            ctx->count_launch();
+        }
+        k_binv_down<F><<<cdiv(lv[1].n, 128), 128, 0, st>>>(lv[0].vals, lv[0].n, lv[0].pre, lv[1].vals);
         ctx->count_launch();
     }
     BB_CUDA(cudaGetLastError());
@@ -632,12 +718,15 @@ int batch_invert_device(bb_ctx* ctx, cudaStream_t st, F* vals, size_t n, F* scra
 
 // How many batched-affine halving rounds an MSM gets: each round needs its own inversion chain
 // (~0.5 ms of latency), so small jobs and thinly filled buckets keep the plain XYZZ path.
-uint32_t choose_affine_rounds(const bb_ctx* ctx, size_t n, uint64_t entries, size_t NB) {
+// Padding a bucket to 2^R entries costs (2^R - 1) / 2 null entries on average, so R follows the mean fill
+// (measured on the 2^20 prove: R = 2 beats R = 3 at 16 entries per bucket, R = 3 wins from 32).
+uint32_t choose_affine_rounds(const bb_ctx* ctx, size_t pairs, uint64_t entries, size_t NB) {
     if (ctx->opt_msm_affine_rounds >= 0) return (uint32_t)(ctx->opt_msm_affine_rounds > 8 ? 8 : ctx->opt_msm_affine_rounds);
-    if (n < (1u << 15)) return 0;
+    if (pairs < (1u << 15)) return 0;
     const uint64_t avg = entries / (NB ? NB : 1);
-    if (avg >= 12) return 3;
-    if (avg >= 6) return 2;
+    if (avg >= 24) return 3;
+    if (avg >= 10) return 2;
+    if (avg >= 5) return 1;
     return 0;
 }
 
@@ -649,7 +738,7 @@ int launch_msm(bb_msm_job* job) {
     const size_t NB = (size_t)W * D;
     const size_t n = job->n;
     const uint64_t entries = (uint64_t)n * W;       // upper bound of the bucket entries (one per non-zero digit)
-    const uint32_t R = job->precomp ? 0u : choose_affine_rounds(ctx, n, entries, NB);
+    const uint32_t R = job->precomp ? 0u : choose_affine_rounds(ctx, job->n_dense, (uint64_t)job->n_dense * W, NB);
     const uint32_t pad_mask = (1u << R) - 1u;
     const uint64_t slots = entries + (uint64_t)NB * pad_mask;   // sorted-array capacity with every bucket padded to 2^R
     if (slots >= (1ull << 32)) { set_error("bb_msm: %zu scalars x %u windows exceed 2^32 bucket entries; split the job", n, W); return BB_ERR_ARG; }
@@ -872,16 +961,16 @@ int bases_build_table(bb_ctx* ctx, bb_bases* b) {
 namespace bb {
 int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint64_t* density_bits, size_t density_len,
               const void* scalars, bool scalars_on_device, size_t n, int form, cudaEvent_t wait_for, bb_msm_job** out,
-              const char* tag, bool critical) {
+              const char* tag, int critical) {
     if (!ctx || !bases || !out || (n && !scalars)) { set_error("bb_msm: null argument"); return BB_ERR_ARG; }
     if (n >= (1ull << 31) || bases->n >= (1ull << 31)) { set_error("bb_msm: more than 2^31 terms"); return BB_ERR_ARG; }
     if (form != BB_FORM_CANONICAL && form != BB_FORM_MONTGOMERY) { set_error("bb_msm: bad form"); return BB_ERR_ARG; }
     BB_CUDA(cudaSetDevice(ctx->device));
     bb_msm_job* job = new bb_msm_job();
     *out = job;
-    job->ctx = ctx; job->bases = bases; job->group = bases->group; job->n = n;
+    job->ctx = ctx; job->bases = bases; job->group = bases->group; job->n = n; job->n_dense = n;
     job->tag = tag;
-    job->st = critical ? ctx->crit_stream : ctx->pick_stream();
+    job->st = critical ? ctx->crit_stream[(critical - 1) & 1] : ctx->pick_stream();
     if (wait_for) BB_CUDA(cudaStreamWaitEvent(job->st, wait_for, 0));
     if (density_bits && density_len != n) {                 // the assert! at multiexp.rs:324-329
         set_error("density map has %zu entries for %zu exponents", density_len, n);
@@ -930,6 +1019,7 @@ int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint
             if (j == words - 1 && (n & 63)) wv &= (1ull << (n & 63)) - 1ull;
             acc += (uint32_t)__builtin_popcountll(wv);
         }
+        job->n_dense = acc;
         if ((s = job->d_density.alloc(ctx, words * 8)) != BB_OK) return fail(s);
         if ((s = job->d_rank.alloc(ctx, words * 4)) != BB_OK) return fail(s);
         if (words) {

@@ -238,7 +238,7 @@ int prove_partials_impl(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, uin
     int s = BB_OK;
     static const char* const job_tag[8] = {"h", "l", "a_inputs", "a_aux", "b_g1_inputs", "b_g1_aux", "b_g2_inputs", "b_g2_aux"};
     auto start = [&](int slot, const bb_bases* bases, size_t off, const uint64_t* dens, size_t dens_len, const void* d_sc, size_t cnt, cudaEvent_t ev) {
-        if (s == BB_OK) s = msm_start(ctx, bases, off, dens, dens_len, d_sc, true, cnt, BB_FORM_MONTGOMERY, ev, &jobs[slot], job_tag[slot], slot == 0);
+        if (s == BB_OK) s = msm_start(ctx, bases, off, dens, dens_len, d_sc, true, cnt, BB_FORM_MONTGOMERY, ev, &jobs[slot], job_tag[slot], slot == 0 ? 1 : slot == 7 ? 2 : 0);
     };
     // H pipeline first (prover.rs:221-240): it and the h MSM behind it are the longest dependency chain of the
     // proof; both run on high-priority streams, the seven witness MSMs fill the machine around them
@@ -253,13 +253,14 @@ int prove_partials_impl(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, uin
         if (s == BB_OK && cudaEventRecord(ev_h, st) != cudaSuccess) { set_error("cudaEventRecord(H pipeline done) failed"); s = BB_ERR_CUDA; }
         if (s == BB_OK) start(0, crs->h, 0, nullptr, 0, d_a.p, m - 1, ev_h);                                // :238-244
     }
+    // the G2 MSM has the longest chain of the seven (Fp2 arithmetic): it goes first, on the other high-priority stream
+    start(7, crs->b_g2, b_in_total, w->b_aux_density, w->n_aux, d_aux.p, w->n_aux, ev_up);                  // :318
     start(1, crs->l, 0, nullptr, 0, d_aux.p, w->n_aux, ev_up);                                              // :263-268
     start(2, crs->a, 0, nullptr, 0, d_in.p, w->n_inputs, ev_up);                                            // :275-280
     start(3, crs->a, w->n_inputs, w->a_aux_density, w->n_aux, d_aux.p, w->n_aux, ev_up);                    // :281-286
     start(4, crs->b_g1, 0, w->b_input_density, w->n_inputs, d_in.p, w->n_inputs, ev_up);                    // :296-301
     start(5, crs->b_g1, b_in_total, w->b_aux_density, w->n_aux, d_aux.p, w->n_aux, ev_up);                  // :302-307
     start(6, crs->b_g2, 0, w->b_input_density, w->n_inputs, d_in.p, w->n_inputs, ev_up);                    // :312-317
-    start(7, crs->b_g2, b_in_total, w->b_aux_density, w->n_aux, d_aux.p, w->n_aux, ev_up);                  // :318
     if (while_device_runs && *while_device_runs) (*while_device_runs)();
     // wait() x8 (prover.rs:339-354); always drain every started job.  The h MSM was queued last
     // (it follows the H pipeline), so it is waited for last: the host-side window folds of the

@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--precompute", type=int, default=0, help="1 = resident window multiples of every base vector (msm_precompute)")
     ap.add_argument("--acc-variant", type=int, default=0)
+    ap.add_argument("--ntt-radix8", type=int, default=1, help="0 = radix-2 sweeps in shared memory (k_ntt_pass) instead of register radix-8 windows")
     ap.add_argument("--affine-rounds", type=int, default=-1, help="batched-affine halving rounds per MSM (-1 = by size, 0 = XYZZ accumulation only)")
     ap.add_argument("--affine-batch", type=int, default=0, help="pairs per thread in the batched-affine rounds (0 = default)")
     ap.add_argument("--reduce-k", type=int, default=0)
@@ -298,6 +299,7 @@ def run_prove(args):
     if args.acc_variant:
         worker.set_option("msm_acc_variant", args.acc_variant)
     worker.set_option("msm_affine_rounds", args.affine_rounds)
+    worker.set_option("ntt_radix8", args.ntt_radix8)
     if args.affine_batch:
         worker.set_option("msm_affine_batch", args.affine_batch)
     log("synthesising the MiMC-chain witness (CPU, product-side generator)")
@@ -538,6 +540,7 @@ def run_ntt(args):
     log_n = args.log_size or 24
     n = 1 << log_n
     worker = bb.Worker(0)
+    worker.set_option("ntt_radix8", args.ntt_radix8)
     d = worker.device_alloc(n * 32)
     bb.synth_scalars_device(worker, 41, n, d)
     v = np.zeros((n, 4), np.uint64)
