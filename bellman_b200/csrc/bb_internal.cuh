@@ -61,6 +61,7 @@ struct bb_ctx {
     long opt_msm_big_cap = 0;
     long opt_shard_windows = 4;      // multi-GPU: up to this many window shards per base range (1 = base ranges only)
     long opt_msm_affine_rounds = -1;  // batched-affine halving rounds per MSM: -1 = by size, 0 = none (XYZZ accumulation only)
+    long opt_msm_affine_tma = 0;      // dense halving rounds of G1 jobs: operands staged by cp.async.bulk + mbarrier (k_aff_phase3_tma)
     long opt_msm_affine_batch = 16;   // pairs per thread sharing one link of the inversion chain
     long opt_msm_precompute = 0;     // resident window multiples 2^(c w) P of every base vector (msm.cu: bases_build_table)
     struct ProfEntry { double ms = 0; uint64_t launches = 0, units = 0; };

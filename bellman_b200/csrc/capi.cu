@@ -322,6 +322,7 @@ int bb_ctx_set_option(bb_ctx* ctx, const char* key, long value) {
     else if (k == "msm_precompute") ctx->opt_msm_precompute = value;
     else if (k == "msm_affine_rounds") ctx->opt_msm_affine_rounds = value;
     else if (k == "msm_affine_batch") ctx->opt_msm_affine_batch = value;
+    else if (k == "msm_affine_tma") ctx->opt_msm_affine_tma = value;
     else if (k == "shard_windows") { if (value < 1) { set_error("shard_windows >= 1"); return BB_ERR_ARG; } ctx->opt_shard_windows = value; }
     else if (k == "msm_reduce_k1") { if (value < 2 || (value & (value - 1))) { set_error("msm_reduce_k1 must be a power of two >= 2"); return BB_ERR_ARG; } ctx->opt_msm_reduce_k1 = value; }
     else if (k == "msm_reduce_k") { if (value < 2 || (value & (value - 1))) { set_error("msm_reduce_k must be a power of two >= 2"); return BB_ERR_ARG; } ctx->opt_msm_reduce_k = value; }

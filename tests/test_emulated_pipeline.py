@@ -97,6 +97,14 @@ def test_emulated_affine_rounds_special(worker):
         force(-1)
 
 
+def test_emulated_affine_rounds_tma_variant(worker):
+    force = _force_affine(worker)
+    try:
+        G.test_affine_rounds_tma_staged_variant(worker, force)
+    finally:
+        force(-1)
+
+
 def _force_affine(worker):
     def force(rounds, batch=16):
         worker.set_option("msm_affine_rounds", rounds)

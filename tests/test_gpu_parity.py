@@ -535,6 +535,21 @@ def test_affine_rounds_special_pairs(worker, affine):
     assert rc == 0 and np.array_equal(_gpu_multiexp(worker, bb.G1, b2, 7, dens, e), want)
 
 
+def test_affine_rounds_tma_staged_variant(worker, affine):
+    """k_aff_phase3_tma (dense rounds fed by cp.async.bulk + mbarrier) gives the same points as the plain loads."""
+    try:
+        worker.set_option("msm_affine_tma", 1)
+        for n, rounds, batch in ((33, 2, 4), (1000, 3, 16), (3000, 4, 7), (5000, 3, 1)):
+            affine(rounds, batch)
+            bases = o1.g1_fixed_mul(o1.fr_random(1000 + n, n))
+            ex = o1.fr_random(2000 + n, n)
+            rc, want = o1.multiexp(1, bases, 0, None, ex)
+            assert rc == 0 and np.array_equal(_gpu_multiexp(worker, bb.G1, bases, 0, None, ex), want), (n, rounds, batch)
+        test_affine_rounds_special_pairs(worker, affine)
+    finally:
+        worker.set_option("msm_affine_tma", 0)
+
+
 def test_affine_rounds_error_semantics(worker, affine):
     """an identity base under a non-zero digit is still UnexpectedIdentity when the rounds consume it"""
     affine(3)
