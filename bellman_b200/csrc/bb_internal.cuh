@@ -56,6 +56,7 @@ struct bb_ctx {
     long opt_ntt_radix8 = 1;          // register radix-8 windows (k_ntt_pass8) where the tile shape allows; 0 = radix-2 sweeps in shared memory
     long opt_profile = 0;
     long opt_msm_acc_variant = 0;
+    long opt_msm_reduce_2d = 1;      // bucket reduction through row / column sums (k_bucket_fold) for windows of >= 1024 buckets
     long opt_msm_reduce_k = 4;       // entries per thread and level of the bucket reduction: 4 halves the length of the
     long opt_msm_reduce_k1 = 4;      // dependent-addition chain of 16 (2K per level, log_K D levels) for 1.25x its additions
     long opt_msm_big_cap = 0;

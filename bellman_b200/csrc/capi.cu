@@ -224,6 +224,13 @@ __global__ void k_selftest_field(const FE* a, const FE* b, FE* o, size_t n, int 
     FE x = a[i], y = b[i];
     o[i] = op == 0 ? x * y : op == 1 ? x + y : op == 2 ? x - y : x.sqr();
 }
+// Fp only: op 4 = inverse by the binary Euclidean algorithm (what FieldOps<Fp>::inv runs), 5 = a^(p-2); zero -> zero
+__global__ void k_selftest_fp_inv(const Fp* a, Fp* o, size_t n, int op) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp x = a[i];
+    o[i] = x.is_zero() ? x : (op == 4 ? fp_inv_gcd(x) : fp_inv(x));
+}
 template <class F>
 __global__ void k_selftest_point(const Affine<F>* a, const Affine<F>* b, Affine<F>* o, size_t n, int op) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -323,6 +330,7 @@ int bb_ctx_set_option(bb_ctx* ctx, const char* key, long value) {
     else if (k == "msm_affine_rounds") ctx->opt_msm_affine_rounds = value;
     else if (k == "msm_affine_batch") ctx->opt_msm_affine_batch = value;
     else if (k == "msm_affine_tma") ctx->opt_msm_affine_tma = value;
+    else if (k == "msm_reduce_2d") ctx->opt_msm_reduce_2d = value;
     else if (k == "shard_windows") { if (value < 1) { set_error("shard_windows >= 1"); return BB_ERR_ARG; } ctx->opt_shard_windows = value; }
     else if (k == "msm_reduce_k1") { if (value < 2 || (value & (value - 1))) { set_error("msm_reduce_k1 must be a power of two >= 2"); return BB_ERR_ARG; } ctx->opt_msm_reduce_k1 = value; }
     else if (k == "msm_reduce_k") { if (value < 2 || (value & (value - 1))) { set_error("msm_reduce_k must be a power of two >= 2"); return BB_ERR_ARG; } ctx->opt_msm_reduce_k = value; }
@@ -586,6 +594,17 @@ int bb_selftest_field(bb_ctx* ctx, int field, int op, const void* a, const void*
     if (!ctx) return BB_ERR_ARG;
     BB_CUDA(cudaSetDevice(ctx->device));
     if (field == 0) return selftest_run<Fr>(ctx, k_selftest_field<Fr>, a, b, out, n, op);
+    if (field == 1 && (op == 4 || op == 5)) {
+        DevBuf da, d_o;
+        BB_TRY(da.alloc(ctx, n * sizeof(Fp))); BB_TRY(d_o.alloc(ctx, n * sizeof(Fp)));
+        cudaStream_t st = ctx->main_stream;
+        BB_CUDA(cudaMemcpyAsync(da.p, a, n * sizeof(Fp), cudaMemcpyHostToDevice, st));
+        if (n) { k_selftest_fp_inv<<<cdiv(n, 64), 64, 0, st>>>(da.as<Fp>(), d_o.as<Fp>(), n, op); ctx->count_launch(); }
+        BB_CUDA(cudaGetLastError());
+        BB_CUDA(cudaMemcpyAsync(out, d_o.p, n * sizeof(Fp), cudaMemcpyDeviceToHost, st));
+        BB_CUDA(cudaStreamSynchronize(st));
+        return BB_OK;
+    }
     if (field == 1) return selftest_run<Fp>(ctx, k_selftest_field<Fp>, a, b, out, n, op);
     return BB_ERR_ARG;
 }

@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(128) k_point_tree_sum(const XYZZ<F>* in, uint3
 //   S = A_1 + K_1 (A_2 + K_2 (A_3 + ...)),   A_l = sum_j acc_j at level l,
 // two additions per bucket in total, every level fully parallel.
 template <class F>
-__global__ void __launch_bounds__(128) k_msm_reduce_level(const XYZZ<F>* in, uint32_t D_in, uint32_t K, int one_based,
+__global__ void __launch_bounds__(128) k_msm_reduce_level(const XYZZ<F>* in, uint32_t D_in, uint32_t K, uint32_t one_based_windows,
                                                           XYZZ<F>* run_out, XYZZ<F>* acc_partials) {
     extern __shared__ uint4 shraw[];
     XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(shraw);
@@ -377,11 +377,43 @@ __global__ void __launch_bounds__(128) k_msm_reduce_level(const XYZZ<F>* in, uin
             acc.add(running);
         }
         running.add(ld_words(B));
-        if (one_based) acc.add(running);
+        if (w < one_based_windows) acc.add(running);      // weights t + 1 instead of t
         st_words(run_out + (size_t)w * runs + j, running);
     }
     block_tree_reduce(acc, sh);
     if (threadIdx.x == 0) st_words(acc_partials + (size_t)w * gridDim.x + blockIdx.x, acc);
+}
+
+// ---- two-dimensional bucket reduction ---------------------------------------------------------------
+// The weights of a window's D buckets are 1..D.  Write the bucket index as d = hi * Lo + lo: then
+//   sum_d (d + 1) B_d = sum_lo (lo + 1) C_lo + Lo * sum_hi hi R_hi,
+// with the column sums C_lo = sum_hi B[hi][lo] and the row sums R_hi = sum_lo B[hi][lo].  Row and column sums
+// are plain sums -- trees of independent additions over the whole array, D additions each, every level a full
+// grid -- and only the two short weighted sums (Lo and D / Lo entries per window) are left for the serial
+// recursion below.  Same two additions per bucket as the running-sum form (multiexp.rs:271-275), but the long
+// dependent chains (2K additions per thread and level over D / K threads) shrink to chains over sqrt(D) entries.
+//
+// out[w][o] = sum_{k < folds} in[w][a * inner_in + b + k * kstride],  o = a * inner_out + b, b < inner_out
+template <class F>
+__global__ void __launch_bounds__(128) k_bucket_fold(const XYZZ<F>* in, XYZZ<F>* out, uint32_t n_out, uint32_t in_window, uint32_t out_window,
+                                                     uint32_t inner_out, uint32_t inner_in, uint32_t kstride, uint32_t folds) {
+    const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x, w = blockIdx.y;
+    if (o >= n_out) return;
+    const uint32_t a = o / inner_out, b = o - a * inner_out;
+    const XYZZ<F>* src = in + (size_t)w * in_window + (size_t)a * inner_in + b;
+    XYZZ<F> acc = ld_words(src);
+    for (uint32_t k = 1; k < folds; k++) acc.add(ld_words(src + (size_t)k * kstride));
+    st_words(out + (size_t)w * out_window + o, acc);
+}
+// out[w] = sc[w] + 2^shift * sr[w]
+template <class F>
+__global__ void __launch_bounds__(32) k_bucket_fold_combine(const XYZZ<F>* sums, uint32_t W, uint32_t shift, XYZZ<F>* out) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    XYZZ<F> r = ld_words(sums + W + w);
+    for (uint32_t k = 0; k < shift; k++) r = r.dbl();
+    r.add(ld_words(sums + w));
+    st_words(out + w, r);
 }
 
 // S_w = A_1[w] + K_1 (A_2[w] + K_2 (A_3[w] + ...)); level sums are stored level-major: A[l*W + w]
@@ -514,7 +546,7 @@ struct bb_msm_job {
     int status = BB_OK;              // pre-launch failure, reported at wait()
     const char* tag = nullptr;       // profile mode: name of this job in the prover's timeline
     DigitArgs dargs{};
-    DevBuf d_scalars, d_density, d_rank, d_counts, d_offsets, d_tiles, d_sorted, d_order, d_buckets, d_partials, d_runs, d_levels, d_onesp, d_final, d_ones, d_err, d_big, d_tasks, d_biglist, d_tasksums, d_aff0, d_aff1, d_pre, d_tp, d_doffsets;
+    DevBuf d_scalars, d_density, d_rank, d_counts, d_offsets, d_tiles, d_sorted, d_order, d_buckets, d_partials, d_runs, d_levels, d_onesp, d_final, d_ones, d_err, d_big, d_tasks, d_biglist, d_tasksums, d_aff0, d_aff1, d_pre, d_tp, d_doffsets, d_fold;
     std::vector<uint32_t> h_rank;
     void* h_out = nullptr;           // pinned: [W window sums][1 ones sum] then err[4]
     size_t h_out_bytes = 0;
@@ -542,7 +574,7 @@ uint32_t choose_window(bb_ctx* ctx, size_t n) {
 // Runs the multi-level bucket reduction for W windows of D buckets; window sums -> out[0..W)
 template <class F>
 int reduce_buckets(bb_ctx* ctx, cudaStream_t st, const XYZZ<F>* buckets, uint32_t W, uint32_t D, uint32_t K0, uint32_t K1,
-                   DevBuf& d_runs, DevBuf& d_partials, DevBuf& d_levels, XYZZ<F>* out) {
+                   DevBuf& d_runs, DevBuf& d_partials, DevBuf& d_levels, XYZZ<F>* out, uint32_t one_based_windows = 0xffffffffu) {
     struct Level { uint32_t D_in, K, runs, nblk; };
     std::vector<Level> lv;
     for (uint32_t d = D;;) {
@@ -574,7 +606,7 @@ int reduce_buckets(bb_ctx* ctx, cudaStream_t st, const XYZZ<F>* buckets, uint32_
     size_t part_off = 0;
     for (size_t l = 0; l < lv.size(); l++) {
         const Level& L = lv[l];
-        k_msm_reduce_level<F><<<dim3(L.nblk, W), 128, sh, st>>>(in, L.D_in, L.K, l == 0 ? 1 : 0, runs, parts + part_off);
+        k_msm_reduce_level<F><<<dim3(L.nblk, W), 128, sh, st>>>(in, L.D_in, L.K, l == 0 ? one_based_windows : 0u, runs, parts + part_off);
         ctx->count_launch();
         uint32_t lg = 0;
         while ((1u << lg) < L.K) lg++;
@@ -588,6 +620,60 @@ int reduce_buckets(bb_ctx* ctx, cudaStream_t st, const XYZZ<F>* buckets, uint32_
     k_msm_level_sums<F><<<dim3(W, RL.n), 128, sh, st>>>(parts, W, RL, levels);
     ctx->count_launch();
     k_msm_reduce_combine<F><<<cdiv(W, 32), 32, 0, st>>>(levels, W, RL, out);
+    ctx->count_launch();
+    BB_CUDA(cudaGetLastError());
+    return BB_OK;
+}
+
+// Window sums of W windows of D buckets each (XYZZ, CLOBBERED).  Large windows go through the two-dimensional
+// form: row sums into `fold`, column sums in place, then one run of the serial recursion over 2 W short arrays.
+template <class F>
+int reduce_buckets_2d(bb_ctx* ctx, cudaStream_t st, XYZZ<F>* buckets, uint32_t W, uint32_t D, uint32_t K0, uint32_t K1,
+                      DevBuf& d_fold, DevBuf& d_runs, DevBuf& d_partials, DevBuf& d_levels, XYZZ<F>* out) {
+    uint32_t lg = 0;
+    while ((1u << lg) < D) lg++;
+    if (!ctx->opt_msm_reduce_2d || D < 1024 || (1u << lg) != D) return reduce_buckets<F>(ctx, st, buckets, W, D, K0, K1, d_runs, d_partials, d_levels, out);
+    const uint32_t lo_bits = (lg + 1) / 2, Lo = 1u << lo_bits, H = D >> lo_bits;       // Lo >= H
+    // small[0..W) = column sums (Lo each, weights lo + 1), small[W..2W) = row sums (H each, padded to Lo, weights hi)
+    BB_TRY(d_fold.alloc(ctx, ((size_t)W * D / 2 + (size_t)W * D / 4 + (size_t)2 * W * Lo + 2 * (size_t)W) * sizeof(XYZZ<F>)));
+    XYZZ<F>* rowbuf[2] = {d_fold.as<XYZZ<F>>(), d_fold.as<XYZZ<F>>() + (size_t)W * D / 2};
+    XYZZ<F>* small = rowbuf[1] + (size_t)W * D / 4;
+    XYZZ<F>* sums = small + (size_t)2 * W * Lo;
+    auto folds_of = [](uint32_t len) { return len % 4 == 0 && len >= 4 ? 4u : 2u; };
+    // rows first (they read the untouched buckets): [H][Lo] -> [H][Lo / f] -> ... -> [H][1]; a row fold
+    // compacts the rows, so it cannot run in place: two scratch buffers take turns
+    {
+        const XYZZ<F>* in = buckets;
+        uint32_t in_window = D, len = Lo, turn = 0;
+        while (len > 1) {
+            const uint32_t f = folds_of(len), nl = len / f, n_out = H * nl;
+            const bool last = nl == 1;
+            XYZZ<F>* dst = last ? small + (size_t)W * Lo : rowbuf[turn];
+            const uint32_t out_window = last ? Lo : n_out;
+            k_bucket_fold<F><<<dim3(cdiv(n_out, 128), W), 128, 0, st>>>(in, dst, n_out, in_window, out_window, nl, len, nl, f);
+            ctx->count_launch();
+            in = dst; in_window = out_window; len = nl; turn ^= 1u;
+        }
+        if (H < Lo) BB_CUDA(cudaMemset2DAsync(small + (size_t)W * Lo + H, (size_t)Lo * sizeof(XYZZ<F>), 0, (size_t)(Lo - H) * sizeof(XYZZ<F>), W, st));   // identity padding
+    }
+    // columns in place: [H][Lo] -> [H / f][Lo] -> ... -> [1][Lo]
+    {
+        uint32_t rows = H;
+        XYZZ<F>* cur = buckets;
+        uint32_t in_window = D;
+        while (rows > 1) {
+            const uint32_t f = folds_of(rows), nr = rows / f, n_out = nr * Lo;
+            const bool last = nr == 1;
+            XYZZ<F>* dst = last ? small : cur;
+            const uint32_t out_window = last ? Lo : in_window;
+            k_bucket_fold<F><<<dim3(cdiv(n_out, 128), W), 128, 0, st>>>(cur, dst, n_out, in_window, out_window, n_out, n_out, n_out, f);
+            ctx->count_launch();
+            cur = dst; in_window = out_window; rows = nr;
+        }
+        if (H == 1) BB_CUDA(cudaMemcpy2DAsync(small, (size_t)Lo * sizeof(XYZZ<F>), buckets, (size_t)D * sizeof(XYZZ<F>), (size_t)Lo * sizeof(XYZZ<F>), W, cudaMemcpyDeviceToDevice, st));
+    }
+    BB_TRY(reduce_buckets<F>(ctx, st, small, 2 * W, Lo, K0, K1, d_runs, d_partials, d_levels, sums, W));
+    k_bucket_fold_combine<F><<<cdiv(W, 32), 32, 0, st>>>(sums, W, lo_bits, out);
     ctx->count_launch();
     BB_CUDA(cudaGetLastError());
     return BB_OK;
@@ -970,7 +1056,7 @@ int launch_msm(bb_msm_job* job) {
         BB_STAGE("fold slots");
     }
     job->W_out = Wr;
-    BB_TRY(reduce_buckets<F>(ctx, st, buckets, Wr, D, (uint32_t)ctx->opt_msm_reduce_k, (uint32_t)ctx->opt_msm_reduce_k1, job->d_runs, job->d_partials, job->d_levels, fin));
+    BB_TRY(reduce_buckets_2d<F>(ctx, st, buckets, Wr, D, (uint32_t)ctx->opt_msm_reduce_k, (uint32_t)ctx->opt_msm_reduce_k1, job->d_fold, job->d_runs, job->d_partials, job->d_levels, fin));
     size_t sh = 128 * sizeof(XYZZ<F>);
     if (sh > 48 * 1024) BB_CUDA(cudaFuncSetAttribute(k_msm_sum_list<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
     BB_TRY(job->d_onesp.alloc(ctx, ONES_BLOCKS * sizeof(XYZZ<F>)));
@@ -1260,7 +1346,8 @@ int bb_selftest_bucket_reduce(bb_ctx* ctx, const void* affine_pts, uint32_t D, u
     BB_TRY(d_b.alloc(ctx, D * sizeof(G1X))); BB_TRY(d_f.alloc(ctx, sizeof(G1X)));
     cudaStream_t st = ctx->main_stream;
     BB_CUDA(cudaMemcpyAsync(d_b.p, h.data(), D * sizeof(G1X), cudaMemcpyHostToDevice, st));
-    BB_TRY(reduce_buckets<Fp>(ctx, st, d_b.as<G1X>(), 1, D, K, K, d_r, d_p, d_l, d_f.as<G1X>()));
+    DevBuf d_fold;                                       // D >= 1024 takes the two-dimensional form unless msm_reduce_2d = 0
+    BB_TRY(reduce_buckets_2d<Fp>(ctx, st, d_b.as<G1X>(), 1, D, K, K, d_fold, d_r, d_p, d_l, d_f.as<G1X>()));
     G1X r;
     BB_CUDA(cudaMemcpyAsync(&r, d_f.p, sizeof r, cudaMemcpyDeviceToHost, st));
     BB_CUDA(cudaStreamSynchronize(st));

@@ -154,6 +154,10 @@ __global__ void __launch_bounds__(256) k_ntt_pass(PassArgs A) {
     }
 }
 
+// out-of-line Fr product for the fully unrolled radix-8 kernel: 12 inlined products per window made the kernel
+// ~15 K instructions and ncu showed it starved by instruction-cache misses (no_instruction 2.3 warps per issue)
+static __device__ __noinline__ Fr fr_mul_outlined(Fr a, Fr b) { return a * b; }
+
 // The same pass with radix-8 butterflies held in registers: a thread owns 8 elements that differ in three
 // consecutive row bits, runs those three stages on them without touching shared memory, and the tile is
 // exchanged through shared memory only between such windows (k = 8 stages: windows [0,3) [3,6) [5,8), the
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(256) k_ntt_pass8(PassArgs A) {
                 Fr y = x[v];
                 if (s != 0) {
                     const uint32_t j = addr(e0 | (u << sh)) & ((1u << s) - 1u);
-                    y = y * ld_fr(A.tw + ((size_t)j << (A.log_n - s - 1u)));
+                    y = fr_mul_outlined(y, ld_fr(A.tw + ((size_t)j << (A.log_n - s - 1u))));
                 }
                 Fr a = x[u];
                 x[u] = a + y;

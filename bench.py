@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--precompute", type=int, default=0, help="1 = resident window multiples of every base vector (msm_precompute)")
     ap.add_argument("--acc-variant", type=int, default=0)
     ap.add_argument("--ntt-radix8", type=int, default=1, help="0 = radix-2 sweeps in shared memory (k_ntt_pass) instead of register radix-8 windows")
+    ap.add_argument("--reduce-2d", type=int, default=1, help="0 = serial running-sum recursion over whole windows instead of row/column sums first")
+    ap.add_argument("--affine-tma", type=int, default=0, help="1 = dense halving rounds of G1 jobs staged by cp.async.bulk + mbarrier")
     ap.add_argument("--affine-rounds", type=int, default=-1, help="batched-affine halving rounds per MSM (-1 = by size, 0 = XYZZ accumulation only)")
     ap.add_argument("--affine-batch", type=int, default=0, help="pairs per thread in the batched-affine rounds (0 = default)")
     ap.add_argument("--reduce-k", type=int, default=0)
@@ -299,6 +301,8 @@ def run_prove(args):
     if args.acc_variant:
         worker.set_option("msm_acc_variant", args.acc_variant)
     worker.set_option("msm_affine_rounds", args.affine_rounds)
+    worker.set_option("msm_reduce_2d", args.reduce_2d)
+    worker.set_option("msm_affine_tma", args.affine_tma)
     worker.set_option("ntt_radix8", args.ntt_radix8)
     if args.affine_batch:
         worker.set_option("msm_affine_batch", args.affine_batch)
@@ -484,6 +488,8 @@ def run_msm(args):
     if args.precompute:
         worker.set_option("msm_precompute", 1)
     worker.set_option("msm_affine_rounds", args.affine_rounds)
+    worker.set_option("msm_reduce_2d", args.reduce_2d)
+    worker.set_option("msm_affine_tma", args.affine_tma)
     if args.affine_batch:
         worker.set_option("msm_affine_batch", args.affine_batch)
     log("generating bases and scalars on the device")

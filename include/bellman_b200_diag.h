@@ -29,7 +29,8 @@ int bb_synth_mimc_witness(size_t rounds, uint64_t seed, uint64_t* a, uint64_t* b
                           uint64_t* b_input_density, uint64_t* b_aux_density);
 
 /* ---- diagnostics (used by the parity tests; not part of the bellman-facing surface) ------ */
-/* element-wise on the device: field 0 = Fr, 1 = Fp (Montgomery); op 0 mul, 1 add, 2 sub, 3 sqr */
+/* element-wise on the device: field 0 = Fr, 1 = Fp (Montgomery); op 0 mul, 1 add, 2 sub, 3 sqr;
+ * Fp only: 4 = inverse by the binary Euclidean algorithm (fp_inv_gcd), 5 = inverse as a^(p-2); 0 -> 0 */
 int bb_selftest_field(bb_ctx* ctx, int field, int op, const void* a, const void* b, void* out, size_t n);
 /* element-wise on affine points: op 0: a + b (mixed add); 1: 2a + b; 2: a + (2b - b) */
 int bb_selftest_point(bb_ctx* ctx, int group, int op, const void* a, const void* b, void* out, size_t n);

@@ -39,6 +39,7 @@ def worker(emu_lib):
 
 def test_emulated_field_and_point_kernels(worker):
     G.test_field_arithmetic(worker)
+    G.test_fp_inversion_both_ways(worker)
     G.test_point_arithmetic(worker)
     G.test_bucket_reduction_kernels(worker)
 

@@ -64,6 +64,19 @@ def test_field_arithmetic(worker):
         assert np.array_equal(_selftest_field(worker, field, 3, a, b), mul(a, a))
 
 
+def test_fp_inversion_both_ways(worker):
+    """fp_inv_gcd (binary Euclid on the raw limbs, what the batched-affine rounds and to_affine use) and the
+    Fermat power a^(p-2) against python's pow()."""
+    rng = random.Random(22)
+    xs = [1, 2, 3, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, 1 << 380, (1 << 381) - 1 - ((1 << 381) - 1) // P * 0, (1 << 64) - 1, 1 << 32] + \
+         [rng.randrange(1, P) for _ in range(3000)] + [rng.randrange(1, 1 << 40) for _ in range(50)]
+    xs = [x % P or 1 for x in xs]
+    a = o1.fp_from_ints(xs + [0])
+    want = o1.fp_from_ints([pow(x, -1, P) for x in xs] + [0])
+    for op in (4, 5):
+        assert np.array_equal(_selftest_field(worker, 1, op, a, a), want), op
+
+
 def test_point_arithmetic(worker):
     ks = o1.fr_random(31, 64)
     ks2 = o1.fr_random(32, 64)
@@ -93,7 +106,9 @@ def test_bucket_reduction_kernels(worker):
     """sum_d d * B_d (multiexp.rs:271-275) through the multi-level reduction, every level shape."""
     lib = bb.load_library()
     rng = random.Random(33)
-    for D, K in ((1, 8), (2, 8), (8, 8), (64, 2), (64, 8), (512, 16), (4096, 8), (4096, 4), (32768, 8)):
+    for D, K, two_d in ((1, 8, 1), (2, 8, 1), (8, 8, 1), (64, 2, 1), (64, 8, 1), (512, 16, 1), (1024, 4, 1), (2048, 16, 1), (4096, 8, 1),
+                        (4096, 4, 0), (8192, 4, 1), (32768, 8, 0), (32768, 16, 1)):
+        worker.set_option("msm_reduce_2d", two_d)        # 1: windows of >= 1024 buckets go through row / column sums
         ks = [rng.randrange(R) for _ in range(D)]
         for i in range(0, D, 7):
             ks[i] = 0                                   # empty buckets
@@ -103,7 +118,8 @@ def test_bucket_reduction_kernels(worker):
                                            out.ctypes.data_as(C.c_void_p))
         assert rc == 0
         want = o1.g1_fixed_mul(o1.fr_from_ints([sum((i + 1) * k for i, k in enumerate(ks)) % R]))
-        assert np.array_equal(out, want), (D, K)
+        assert np.array_equal(out, want), (D, K, two_d)
+    worker.set_option("msm_reduce_2d", 1)
 
 
 # --------------------------------------------------------------------------------------------
