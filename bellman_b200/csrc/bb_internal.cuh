@@ -53,7 +53,8 @@ struct bb_ctx {
     long opt_msm_window_bits = 0;
     long opt_ntt_tile_log = 11;
     long opt_ntt_col_bits = 3;
-    long opt_ntt_radix8 = 1;          // register radix-8 windows (k_ntt_pass8) where the tile shape allows; 0 = radix-2 sweeps in shared memory
+    long opt_ntt_radix8 = 0;          // 1 = register radix-8 windows (k_ntt_pass8); measured 4-5 % slower than the radix-2 sweeps on B200
+                                      // (2^24 fwd+inv 9.74 vs 9.34 ms, profiles/ab_r02_call4.txt), so it stays an option
     long opt_profile = 0;
     long opt_msm_acc_variant = 0;
     long opt_msm_reduce_2d = 1;      // bucket reduction through row / column sums (k_bucket_fold) for windows of >= 1024 buckets

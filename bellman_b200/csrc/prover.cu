@@ -31,7 +31,12 @@ void shard_policy(const bb_ctx* ctx, uint32_t idx, uint32_t cnt, uint32_t* b, ui
 }
 
 // scalar multiplication on the host (the five Affine * Fr of prover.rs:326-337 and the two
-// MulAssign<Fr> of :342,351); k is a canonical little-endian 256-bit integer
+// MulAssign<Fr> of :342,351); k is a canonical little-endian 256-bit integer.
+// NOT constant time: the window value indexes the table and a zero window skips its addition, and the XYZZ
+// formulas branch on special cases.  The scalars here are the proof's blinding factors r, s (and r s); the
+// reference multiplies with the bls12_381 crate's constant-time routine.  A deployment that shares the host
+// with untrusted code should keep that property by doing these seven products in its own (Rust) layer and
+// handing the points in -- bb_groth16_finalize_with() takes them as the opaque `static` block.
 template <class F>
 XYZZ<F> host_mul(const XYZZ<F>& p, const uint32_t* k) {
     // 4-bit fixed window

@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--precompute", type=int, default=0, help="1 = resident window multiples of every base vector (msm_precompute)")
     ap.add_argument("--acc-variant", type=int, default=0)
-    ap.add_argument("--ntt-radix8", type=int, default=1, help="0 = radix-2 sweeps in shared memory (k_ntt_pass) instead of register radix-8 windows")
+    ap.add_argument("--ntt-radix8", type=int, default=0, help="1 = register radix-8 windows (k_ntt_pass8) instead of radix-2 sweeps in shared memory (k_ntt_pass)")
     ap.add_argument("--reduce-2d", type=int, default=1, help="0 = serial running-sum recursion over whole windows instead of row/column sums first")
     ap.add_argument("--affine-tma", type=int, default=0, help="1 = dense halving rounds of G1 jobs staged by cp.async.bulk + mbarrier")
     ap.add_argument("--affine-rounds", type=int, default=-1, help="batched-affine halving rounds per MSM (-1 = by size, 0 = XYZZ accumulation only)")

@@ -208,7 +208,9 @@ int bb_groth16_finalize(const bb_crs* crs, const uint8_t* partials, size_t count
  * (delta*r, delta*s, delta*rs, alpha*s, beta*r -- prover.rs:326-337) can run on a host thread while
  * the devices compute the partial sums: finalize_static fills BB_PROOF_STATIC_BYTES opaque bytes,
  * finalize_with consumes them.  bb_groth16_finalize == finalize_static + finalize_with;
- * bb_groth16_prove overlaps them internally. */
+ * bb_groth16_prove overlaps them internally.
+ * Side channels: the host-side scalar multiplications by r, s and r s are NOT constant time (windowed
+ * double-and-add with table lookups); the reference uses bls12_381's constant-time multiplication there. */
 #define BB_PROOF_STATIC_BYTES 768
 int bb_groth16_finalize_static(const bb_crs* crs, const uint8_t r[32], const uint8_t s[32], uint8_t* static_out);
 int bb_groth16_finalize_with(const bb_crs* crs, const uint8_t* partials, size_t count, const uint8_t r[32],

@@ -165,7 +165,7 @@ def test_ntt_register_radix8_equals_radix2_sweeps(worker):
                     [dom.fft, dom.ifft, dom.coset_fft, dom.icoset_fft][mode]()
                     assert np.array_equal(dom.into_coeffs(), want), (log_n, mode, r8)
     finally:
-        worker.set_option("ntt_radix8", 1)
+        worker.set_option("ntt_radix8", 0)
 
 
 def test_ntt_padding_and_degree_limit(worker):
