@@ -884,7 +884,9 @@ int batch_invert_device(bb_ctx* ctx, cudaStream_t st, F* vals, size_t n, F* scra
 // (measured on the 2^20 prove: R = 2 beats R = 3 at 16 entries per bucket, R = 3 wins from 32).
 uint32_t choose_affine_rounds(const bb_ctx* ctx, size_t pairs, uint64_t entries, size_t NB) {
     if (ctx->opt_msm_affine_rounds >= 0) return (uint32_t)(ctx->opt_msm_affine_rounds > 8 ? 8 : ctx->opt_msm_affine_rounds);
-    if (pairs < (1u << 15)) return 0;
+    // every round puts an inversion chain (~0.3 ms of dependent latency) on the job's critical path: a job
+    // whose whole accumulation is shorter than that (a small shard of a multi-GPU prove) keeps the XYZZ kernel
+    if (pairs < (1u << 15) || entries < (3u << 20)) return 0;
     const uint64_t avg = entries / (NB ? NB : 1);
     if (avg >= 24) return 3;
     if (avg >= 10) return 2;

@@ -426,6 +426,33 @@ int h_poly_device(bb_ctx* ctx, cudaStream_t st, Fr* d_a, Fr* d_b, Fr* d_c, Fr* d
     return run_passes(ctx, st, d_a, d_a, d_tmp, log_m, tw_i, fin);
 }
 
+// The two halves of h_poly_device for the multi-GPU split by polynomial: the coset evaluations of one
+// polynomial (ifft with the coset shift fused, then fft) ...
+int h_poly_evals_device(bb_ctx* ctx, cudaStream_t st, Fr* d_p, Fr* d_tmp, uint32_t log_m) {
+    if (log_m >= (uint32_t)bbc::FR_S) { set_error("2^%u-point domain: PolynomialDegreeTooLarge", log_m); return BB_ERR_POLYNOMIAL_DEGREE_TOO_LARGE; }
+    NttTables* t = nullptr;
+    const Fr *tw_f = nullptr, *tw_i = nullptr, *gm = nullptr;
+    BB_TRY(get_table(ctx, st, log_m, T_TW_FWD, &t, &tw_f));
+    BB_TRY(get_table(ctx, st, log_m, T_TW_INV, &t, &tw_i));
+    BB_TRY(get_table(ctx, st, log_m, T_POW_G_MINV, &t, &gm));
+    Fusion inv;
+    inv.post = gm;
+    BB_TRY(run_passes(ctx, st, d_p, d_p, d_tmp, log_m, tw_i, inv));
+    Fusion fwd;
+    return run_passes(ctx, st, d_p, d_p, d_tmp, log_m, tw_f, fwd);
+}
+// ... and the last transform over three evaluation vectors (result in d_a)
+int h_poly_final_device(bb_ctx* ctx, cudaStream_t st, Fr* d_a, const Fr* d_b, const Fr* d_c, Fr* d_tmp, uint32_t log_m) {
+    if (log_m >= (uint32_t)bbc::FR_S) { set_error("2^%u-point domain: PolynomialDegreeTooLarge", log_m); return BB_ERR_POLYNOMIAL_DEGREE_TOO_LARGE; }
+    NttTables* t = nullptr;
+    const Fr *tw_i = nullptr, *gz = nullptr;
+    BB_TRY(get_table(ctx, st, log_m, T_TW_INV, &t, &tw_i));
+    BB_TRY(get_table(ctx, st, log_m, T_POW_GINV_MINV_ZINV, &t, &gz));
+    Fusion fin;
+    fin.src_b = d_b; fin.src_c = d_c; fin.post = gz;
+    return run_passes(ctx, st, d_a, d_a, d_tmp, log_m, tw_i, fin);
+}
+
 int domain_pointwise_device(bb_ctx* ctx, cudaStream_t st, Fr* d_a, const Fr* d_b, size_t n, int op, const Fr& k) {
     if (!n) return BB_OK;
     k_domain_pointwise<<<cdiv(n, 256), 256, 0, st>>>(d_a, d_b, n, op, k);

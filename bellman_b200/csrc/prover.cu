@@ -3,7 +3,9 @@
 // multiexps in flight, and the host finalisation.
 #include <chrono>
 #include <functional>
+#include <memory>
 #include <string>
+#include <thread>
 
 #include "bb_internal.cuh"
 
@@ -189,11 +191,76 @@ bool delta_is_identity(const bb_crs* crs) {                                     
     return true;
 }
 
-// The eight MSMs and the H pipeline of create_proof (prover.rs:221-318).  `while_device_runs`, if
-// given, is called once everything is queued and before the first wait: host work that needs no
-// MSM result goes there and overlaps the device.
-int prove_partials_impl(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, uint8_t* partials, const std::function<void()>* while_device_runs) {
-    if (!ctx || !crs || !w || !partials) { set_error("bb_groth16_prove_partials: null argument"); return BB_ERR_ARG; }
+}  // namespace
+
+// One proof in flight: what prove_begin queued and prove_end collects.
+struct bb_prove {
+    bb_ctx* ctx = nullptr;
+    const bb_crs* crs = nullptr;
+    bb_witness w{};
+    size_t m = 1, b_in_total = 0;
+    uint32_t log_m = 0;
+    DevBuf d_a, d_b, d_c, d_tmp, d_in, d_aux;
+    cudaStream_t up = nullptr;
+    cudaEvent_t ev_up = nullptr, ev_h = nullptr;
+    bb_msm_job* jobs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int s = BB_OK;
+    bool h_queued = false;
+    ~bb_prove() {
+        // every exit -- error paths included -- first drains every job and the two streams that touch the buffers
+        // above (the DevBufs go back to the cache when this object dies), then destroys the events
+        for (auto& j : jobs) if (j) { MsmResult r; msm_wait_result(j, &r); j = nullptr; }
+        if (ctx) cudaStreamSynchronize(ctx->main_stream);
+        if (up) cudaStreamSynchronize(up);
+        if (ev_up) cudaEventDestroy(ev_up);
+        if (ev_h) cudaEventDestroy(ev_h);
+    }
+};
+
+namespace {
+
+static const char* const job_tag[8] = {"h", "l", "a_inputs", "a_aux", "b_g1_inputs", "b_g1_aux", "b_g2_inputs", "b_g2_aux"};
+
+void prove_start_job(bb_prove* P, int slot, const bb_bases* bases, size_t off, const uint64_t* dens, size_t dens_len, const void* d_sc, size_t cnt, cudaEvent_t ev) {
+    if (P->s == BB_OK)
+        P->s = msm_start(P->ctx, bases, off, dens, dens_len, d_sc, true, cnt, BB_FORM_MONTGOMERY, ev, &P->jobs[slot], job_tag[slot], slot == 0 ? 1 : slot == 7 ? 2 : 0);
+}
+
+// The H pipeline (prover.rs:221-240) on the high-priority main stream and the h MSM behind it.  With `evals`
+// (device buffers of m coset evaluations of a, b, c -- computed elsewhere, bb_h_coset_evals) only the last
+// transform remains: mul_assign, sub_assign, divide_by_z_on_coset, icoset_fft (:232-237).
+int prove_queue_h(bb_prove* P, const void* const* evals) {
+    bb_ctx* ctx = P->ctx;
+    cudaStream_t st = ctx->main_stream;
+    const bb_witness* w = &P->w;
+    const size_t n = w->n_constraints, m = P->m;
+    const cudaMemcpyKind kind = w->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    int s = BB_OK;
+    if (evals) {
+        s = h_poly_final_device(ctx, st, (Fr*)evals[0], (const Fr*)evals[1], (const Fr*)evals[2], P->d_tmp.as<Fr>(), P->log_m);
+    } else {
+        auto stage = [&](DevBuf& d, const void* src) -> int {
+            if (m > n) BB_CUDA(cudaMemsetAsync((char*)d.p + n * 32, 0, (m - n) * 32, st));   // coeffs.resize(m, zero), domain.rs:69
+            if (n) BB_CUDA(cudaMemcpyAsync(d.p, src, n * 32, kind, st));
+            return BB_OK;
+        };
+        if (!w->on_device) ctx->h2d_bytes += 3 * n * 32;
+        if ((s = stage(P->d_a, w->a)) == BB_OK && (s = stage(P->d_b, w->b)) == BB_OK && (s = stage(P->d_c, w->c)) == BB_OK)
+            s = h_poly_device(ctx, st, P->d_a.as<Fr>(), P->d_b.as<Fr>(), P->d_c.as<Fr>(), P->d_tmp.as<Fr>(), P->log_m);
+    }
+    if (s == BB_OK && cudaEventRecord(P->ev_h, st) != cudaSuccess) { set_error("cudaEventRecord(H pipeline done) failed"); s = BB_ERR_CUDA; }
+    if (s != BB_OK) { P->s = s; return s; }
+    prove_start_job(P, 0, P->crs->h, 0, nullptr, 0, evals ? evals[0] : P->d_a.p, m - 1, P->ev_h);             // :238-244
+    P->h_queued = true;
+    return P->s;
+}
+
+// Queues the uploads and the MSMs of one proof (prover.rs:221-318).  h_inline: the H pipeline and the h MSM are
+// queued here, FIRST -- they are the longest dependency chain of the proof and run on high-priority streams, the
+// seven witness MSMs fill the machine around them.  Otherwise prove_end queues them (multi-GPU: the coset
+// evaluations arrive from other ranks while the witness MSMs already run).
+int prove_begin_impl(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, bool h_inline, bb_prove** out) {
+    if (!ctx || !crs || !w || !out) { set_error("bb_groth16_prove: null argument"); return BB_ERR_ARG; }
     BB_CUDA(cudaSetDevice(ctx->device));
     const size_t n = w->n_constraints;
     size_t m = 1;
@@ -208,83 +275,81 @@ int prove_partials_impl(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, uin
         if (!ctx->epoch_ev) BB_CUDA(cudaEventCreate(&ctx->epoch_ev));
         BB_CUDA(cudaEventRecord(ctx->epoch_ev, st));
     }
-    DevBuf d_a, d_b, d_c, d_tmp, d_in, d_aux;
-    BB_TRY(d_a.alloc(ctx, m * 32)); BB_TRY(d_b.alloc(ctx, m * 32)); BB_TRY(d_c.alloc(ctx, m * 32)); BB_TRY(d_tmp.alloc(ctx, m * 32));
-    BB_TRY(d_in.alloc(ctx, w->n_inputs * 32)); BB_TRY(d_aux.alloc(ctx, w->n_aux * 32));
-    // all eight MSMs are in flight before the first wait (prover.rs:244-318)
-    cudaStream_t up = ctx->pick_stream();
+    std::unique_ptr<bb_prove> P(new bb_prove());
+    P->ctx = ctx; P->crs = crs; P->w = *w; P->m = m; P->log_m = log_m;
+    if (h_inline) { BB_TRY(P->d_a.alloc(ctx, m * 32)); BB_TRY(P->d_b.alloc(ctx, m * 32)); BB_TRY(P->d_c.alloc(ctx, m * 32)); }
+    BB_TRY(P->d_tmp.alloc(ctx, m * 32));
+    BB_TRY(P->d_in.alloc(ctx, w->n_inputs * 32)); BB_TRY(P->d_aux.alloc(ctx, w->n_aux * 32));
+    P->up = ctx->pick_stream();
     const cudaMemcpyKind kind = w->on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    if (w->n_inputs) BB_CUDA(cudaMemcpyAsync(d_in.p, w->input_assignment, w->n_inputs * 32, kind, up));
-    if (w->n_aux) BB_CUDA(cudaMemcpyAsync(d_aux.p, w->aux_assignment, w->n_aux * 32, kind, up));
-    if (!w->on_device) ctx->h2d_bytes += (w->n_inputs + w->n_aux + 3 * n) * 32;
-    // every exit below -- error returns included -- first drains the two streams that touch the buffers
-    // above (the DevBufs go back to the cache when this scope ends) and then destroys the events
-    struct Cleanup {
-        cudaStream_t a, b;
-        cudaEvent_t ev_up = nullptr, ev_h = nullptr;
-        ~Cleanup() {
-            cudaStreamSynchronize(a);
-            cudaStreamSynchronize(b);
-            if (ev_up) cudaEventDestroy(ev_up);
-            if (ev_h) cudaEventDestroy(ev_h);
-        }
-    } guard{st, up};
-    BB_CUDA(cudaEventCreateWithFlags(&guard.ev_up, cudaEventDisableTiming));
-    BB_CUDA(cudaEventCreateWithFlags(&guard.ev_h, cudaEventDisableTiming));
-    const cudaEvent_t ev_up = guard.ev_up, ev_h = guard.ev_h;
-    BB_CUDA(cudaEventRecord(ev_up, up));
-    size_t b_in_total = 0;                            // get_total_density, prover.rs:288-291
-    for (size_t j = 0; j < (w->n_inputs + 63) / 64; j++) {
+    if (w->n_inputs) BB_CUDA(cudaMemcpyAsync(P->d_in.p, w->input_assignment, w->n_inputs * 32, kind, P->up));
+    if (w->n_aux) BB_CUDA(cudaMemcpyAsync(P->d_aux.p, w->aux_assignment, w->n_aux * 32, kind, P->up));
+    if (!w->on_device) ctx->h2d_bytes += (w->n_inputs + w->n_aux) * 32;
+    BB_CUDA(cudaEventCreateWithFlags(&P->ev_up, cudaEventDisableTiming));
+    BB_CUDA(cudaEventCreateWithFlags(&P->ev_h, cudaEventDisableTiming));
+    BB_CUDA(cudaEventRecord(P->ev_up, P->up));
+    for (size_t j = 0; j < (w->n_inputs + 63) / 64; j++) {       // get_total_density, prover.rs:288-291
         uint64_t wv = w->b_input_density[j];
         if (j == (w->n_inputs + 63) / 64 - 1 && (w->n_inputs & 63)) wv &= (1ull << (w->n_inputs & 63)) - 1ull;
-        b_in_total += (size_t)__builtin_popcountll(wv);
+        P->b_in_total += (size_t)__builtin_popcountll(wv);
     }
-    bb_msm_job* jobs[8] = {nullptr};
-    int s = BB_OK;
-    static const char* const job_tag[8] = {"h", "l", "a_inputs", "a_aux", "b_g1_inputs", "b_g1_aux", "b_g2_inputs", "b_g2_aux"};
-    auto start = [&](int slot, const bb_bases* bases, size_t off, const uint64_t* dens, size_t dens_len, const void* d_sc, size_t cnt, cudaEvent_t ev) {
-        if (s == BB_OK) s = msm_start(ctx, bases, off, dens, dens_len, d_sc, true, cnt, BB_FORM_MONTGOMERY, ev, &jobs[slot], job_tag[slot], slot == 0 ? 1 : slot == 7 ? 2 : 0);
-    };
-    // H pipeline first (prover.rs:221-240): it and the h MSM behind it are the longest dependency chain of the
-    // proof; both run on high-priority streams, the seven witness MSMs fill the machine around them
-    if (s == BB_OK) {
-        auto stage = [&](DevBuf& d, const void* src) -> int {
-            if (m > n) BB_CUDA(cudaMemsetAsync((char*)d.p + n * 32, 0, (m - n) * 32, st));   // coeffs.resize(m, zero), domain.rs:69
-            if (n) BB_CUDA(cudaMemcpyAsync(d.p, src, n * 32, kind, st));
-            return BB_OK;
-        };
-        if ((s = stage(d_a, w->a)) == BB_OK && (s = stage(d_b, w->b)) == BB_OK && (s = stage(d_c, w->c)) == BB_OK)
-            s = h_poly_device(ctx, st, d_a.as<Fr>(), d_b.as<Fr>(), d_c.as<Fr>(), d_tmp.as<Fr>(), log_m);
-        if (s == BB_OK && cudaEventRecord(ev_h, st) != cudaSuccess) { set_error("cudaEventRecord(H pipeline done) failed"); s = BB_ERR_CUDA; }
-        if (s == BB_OK) start(0, crs->h, 0, nullptr, 0, d_a.p, m - 1, ev_h);                                // :238-244
+    bb_prove* p = P.get();
+    if (h_inline) prove_queue_h(p, nullptr);
+    const cudaEvent_t ev_up = P->ev_up;
+    const size_t b_in_total = P->b_in_total;
+    // all eight MSMs are in flight before the first wait (prover.rs:244-318); the G2 MSM has the longest chain
+    // of the seven (Fp2 arithmetic): it goes first, on the other high-priority stream
+    prove_start_job(p, 7, crs->b_g2, b_in_total, w->b_aux_density, w->n_aux, P->d_aux.p, w->n_aux, ev_up);      // :318
+    prove_start_job(p, 1, crs->l, 0, nullptr, 0, P->d_aux.p, w->n_aux, ev_up);                                  // :263-268
+    prove_start_job(p, 2, crs->a, 0, nullptr, 0, P->d_in.p, w->n_inputs, ev_up);                                // :275-280
+    prove_start_job(p, 3, crs->a, w->n_inputs, w->a_aux_density, w->n_aux, P->d_aux.p, w->n_aux, ev_up);        // :281-286
+    prove_start_job(p, 4, crs->b_g1, 0, w->b_input_density, w->n_inputs, P->d_in.p, w->n_inputs, ev_up);        // :296-301
+    prove_start_job(p, 5, crs->b_g1, b_in_total, w->b_aux_density, w->n_aux, P->d_aux.p, w->n_aux, ev_up);      // :302-307
+    prove_start_job(p, 6, crs->b_g2, 0, w->b_input_density, w->n_inputs, P->d_in.p, w->n_inputs, ev_up);        // :312-317
+    *out = P.release();
+    return BB_OK;                                      // a failure to queue is kept in the state and reported by prove_end
+}
+
+// Queues the H pipeline if prove_begin did not, waits for the eight MSMs and writes the 960-byte partial sums.
+// Frees the state.  `while_device_runs`, if given, is called once everything is queued and before the first
+// wait: host work that needs no MSM result goes there and overlaps the device.
+int prove_end_impl(bb_prove* Praw, const void* const* evals, uint8_t* partials, const std::function<void()>* while_device_runs) {
+    std::unique_ptr<bb_prove> P(Praw);
+    if (!Praw || !partials) { set_error("bb_groth16_prove_end: null argument"); return BB_ERR_ARG; }
+    bb_ctx* ctx = P->ctx;
+    const bb_crs* crs = P->crs;
+    BB_CUDA(cudaSetDevice(ctx->device));
+    if (!P->h_queued && P->s == BB_OK) {
+        if (!evals) { BB_TRY(P->d_a.alloc(ctx, P->m * 32)); BB_TRY(P->d_b.alloc(ctx, P->m * 32)); BB_TRY(P->d_c.alloc(ctx, P->m * 32)); }
+        prove_queue_h(P.get(), evals);
     }
-    // the G2 MSM has the longest chain of the seven (Fp2 arithmetic): it goes first, on the other high-priority stream
-    start(7, crs->b_g2, b_in_total, w->b_aux_density, w->n_aux, d_aux.p, w->n_aux, ev_up);                  // :318
-    start(1, crs->l, 0, nullptr, 0, d_aux.p, w->n_aux, ev_up);                                              // :263-268
-    start(2, crs->a, 0, nullptr, 0, d_in.p, w->n_inputs, ev_up);                                            // :275-280
-    start(3, crs->a, w->n_inputs, w->a_aux_density, w->n_aux, d_aux.p, w->n_aux, ev_up);                    // :281-286
-    start(4, crs->b_g1, 0, w->b_input_density, w->n_inputs, d_in.p, w->n_inputs, ev_up);                    // :296-301
-    start(5, crs->b_g1, b_in_total, w->b_aux_density, w->n_aux, d_aux.p, w->n_aux, ev_up);                  // :302-307
-    start(6, crs->b_g2, 0, w->b_input_density, w->n_inputs, d_in.p, w->n_inputs, ev_up);                    // :312-317
+    int s = P->s;
     if (while_device_runs && *while_device_runs) (*while_device_runs)();
-    // wait() x8 (prover.rs:339-354); always drain every started job.  The h MSM was queued last
-    // (it follows the H pipeline), so it is waited for last: the host-side window folds of the
-    // other seven overlap it.
+    // wait() x8 (prover.rs:339-354); always drain every started job.  Each wait ends with a host-side Horner
+    // fold of the job's window sums (255 doublings: 0.2 ms for G1, 0.5 ms for G2 on one core); jobs tend to
+    // finish together, so the eight waits run on eight short-lived host threads and the folds overlap.
     G1X sums1[6];
     G2X sums2[2];
     for (auto& p1 : sums1) p1 = G1X::identity();
     for (auto& p2 : sums2) p2 = G2X::identity();
-    static const int wait_order[8] = {1, 2, 3, 4, 5, 6, 7, 0};
     int slot_status[8] = {BB_OK, BB_OK, BB_OK, BB_OK, BB_OK, BB_OK, BB_OK, BB_OK};
-    for (int idx = 0; idx < 8; idx++) {
-        const int k = wait_order[idx];
-        if (!jobs[k]) continue;
-        MsmResult r;
-        slot_status[k] = msm_wait_result(jobs[k], &r);
-        if (slot_status[k] == BB_OK) {
-            if (k >= 6) sums2[k - 6] = r.x2;
-            else sums1[k] = r.g1;
+    {
+        std::thread waiters[8];
+        for (int k = 0; k < 8; k++) {
+            if (!P->jobs[k]) continue;
+            bb_msm_job* job = P->jobs[k];
+            P->jobs[k] = nullptr;
+            waiters[k] = std::thread([&, k, job] {
+                cudaSetDevice(ctx->device);
+                MsmResult r;
+                slot_status[k] = msm_wait_result(job, &r);
+                if (slot_status[k] == BB_OK) {
+                    if (k >= 6) sums2[k - 6] = r.x2;
+                    else sums1[k] = r.g1;
+                }
+            });
         }
+        for (auto& t : waiters) if (t.joinable()) t.join();
     }
     if (s == BB_OK) {
         // Which error create_proof reports when several apply: the density assert fires inside the
@@ -310,6 +375,13 @@ int prove_partials_impl(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, uin
         std::memcpy(partials + 576, a2, 2 * 192);
     }
     return s;
+}
+
+int prove_partials_impl(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, uint8_t* partials, const std::function<void()>* while_device_runs) {
+    if (!partials) { set_error("bb_groth16_prove_partials: null argument"); return BB_ERR_ARG; }
+    bb_prove* P = nullptr;
+    BB_TRY(prove_begin_impl(ctx, crs, w, true, &P));
+    return prove_end_impl(P, nullptr, partials, while_device_runs);
 }
 
 // The terms of A, B, C that depend only on the key and on (r, s) -- prover.rs:326-337:
@@ -366,6 +438,41 @@ extern "C" {
 
 int bb_groth16_prove_partials(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, uint8_t* partials) {
     return prove_partials_impl(ctx, crs, w, partials, nullptr);
+}
+
+int bb_groth16_prove_begin(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, bb_prove** out) {
+    return prove_begin_impl(ctx, crs, w, false, out);
+}
+
+int bb_groth16_prove_end(bb_prove* state, const void* d_evals_a, const void* d_evals_b, const void* d_evals_c, uint8_t* partials) {
+    const bool any = d_evals_a || d_evals_b || d_evals_c;
+    if (any && !(d_evals_a && d_evals_b && d_evals_c)) { delete state; set_error("bb_groth16_prove_end: all three evaluation vectors or none"); return BB_ERR_ARG; }
+    const void* ev[3] = {d_evals_a, d_evals_b, d_evals_c};
+    return prove_end_impl(state, any ? ev : nullptr, partials, nullptr);
+}
+
+// from_coeffs (zero padding to m), ifft and coset_fft of ONE of the polynomials a, b, c (prover.rs:225-230) into a
+// device buffer of m Fr; returns when the result is there
+int bb_h_coset_evals(bb_ctx* ctx, const void* poly, size_t n_constraints, int on_device, void* d_out) {
+    if (!ctx || !d_out || (n_constraints && !poly)) { set_error("bb_h_coset_evals: null argument"); return BB_ERR_ARG; }
+    BB_CUDA(cudaSetDevice(ctx->device));
+    size_t m = 1;
+    uint32_t log_m = 0;
+    while (m < n_constraints) {
+        m *= 2;
+        log_m += 1;
+        if (log_m >= (uint32_t)bbc::FR_S) { set_error("PolynomialDegreeTooLarge"); return BB_ERR_POLYNOMIAL_DEGREE_TOO_LARGE; }
+    }
+    cudaStream_t st = ctx->main_stream;
+    DevBuf d_tmp;
+    BB_TRY(d_tmp.alloc(ctx, m * 32));
+    if (m > n_constraints) BB_CUDA(cudaMemsetAsync((char*)d_out + n_constraints * 32, 0, (m - n_constraints) * 32, st));
+    if (n_constraints) BB_CUDA(cudaMemcpyAsync(d_out, poly, n_constraints * 32, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    if (!on_device) ctx->h2d_bytes += n_constraints * 32;
+    int s = h_poly_evals_device(ctx, st, (Fr*)d_out, d_tmp.as<Fr>(), log_m);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (s == BB_OK && e != cudaSuccess) { set_error("bb_h_coset_evals: %s", cudaGetErrorString(e)); s = BB_ERR_CUDA; }
+    return s;
 }
 
 int bb_groth16_finalize(const bb_crs* crs, const uint8_t* partials, size_t count, const uint8_t* r_bytes, const uint8_t* s_bytes,

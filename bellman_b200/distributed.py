@@ -42,25 +42,43 @@ def max_over_ranks(seconds, group=None):
     return float(t.item())
 
 
-def create_proof_sharded(assignment, params, full_vk_params, r, s, device_ptrs=None, group=None):
-    """One proof over all ranks of `group` (create_proof, groth16/src/prover.rs:217-360, with the
-    MSMs sharded): every rank runs prove_partials on its shard, the 960-byte blobs AND each rank's
-    status are all-gathered in the same collective, and rank 0 finalises.  A SynthesisError on any
-    rank is re-raised on every rank (nobody is left waiting in the all-gather).  Returns the 192
-    proof bytes on rank 0, None elsewhere.  `full_vk_params` is any Parameters object of this rank
-    (only its verifying-key elements are read by finalize)."""
+_EVAL_BUFFERS = {}       # (device, m) -> three tensors of m Fr: the coset evaluations of a, b, c on this rank
+
+
+def h_owner(poly_index, world):
+    """Which rank takes polynomial 0 = a, 1 = b, 2 = c through ifft + coset_fft: one each from three ranks on;
+    with two ranks the first takes a and c."""
+    return poly_index % world if world < 3 else poly_index
+
+
+def create_proof_sharded(assignment, params, full_vk_params, r, s, device_ptrs=None, group=None, split_h=True):
+    """One proof over all ranks of `group` (create_proof, groth16/src/prover.rs:217-360, with the MSMs
+    sharded): every rank runs its shard of the eight MSMs, the 960-byte partial sums AND each rank's status and
+    error text are all-gathered in one collective, and rank 0 finalises.  A SynthesisError on any rank is
+    re-raised on every rank (nobody is left waiting in a collective).  Returns the 192 proof bytes on rank
+    0, None elsewhere.  `full_vk_params` is any Parameters object of this rank (only its verifying-key elements
+    are read by finalize).
+
+    split_h: the H pipeline is divided by polynomial instead of being replicated.  Each NTT stays on one GPU:
+    rank h_owner(i) takes polynomial i of (a, b, c) through ifft + coset_fft (two transforms) and broadcasts
+    the m evaluations; every rank then runs the last transform (a b - c, / Z, icoset_fft) itself.  The longest
+    chain drops from seven transforms to three, and a rank uploads only the polynomials it owns.  The seven
+    witness MSMs are queued first and run underneath."""
     import torch
     import torch.distributed as dist
 
     import threading
 
-    from . import BackendError, _ERRORS, finalize, finalize_static, prove_partials
+    from . import BackendError, _ERRORS, finalize, finalize_static, h_coset_evals, prove_begin, prove_end, prove_partials
 
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
     # rank 0: the scalar multiplications of the finalisation that need no MSM result run on a host
     # thread while the devices compute the partial sums
     ahead = {}
     worker_thread = None
-    if dist.get_rank(group) == 0:
+    if rank == 0:
         def _static():
             try:
                 ahead["static"] = finalize_static(full_vk_params, r, s)
@@ -69,14 +87,62 @@ def create_proof_sharded(assignment, params, full_vk_params, r, s, device_ptrs=N
         worker_thread = threading.Thread(target=_static)
         worker_thread.start()
     status, blob, msg = 0, bytes(PARTIALS_BYTES), ""
+    state = None
     try:
-        blob = prove_partials(assignment, params, device_ptrs)
-    except Exception as e:                               # whatever it is, the other ranks must not be left in the all-gather
+        if split_h and world > 1:
+            n = assignment.a.shape[0]
+            m = 1
+            while m < n:
+                m *= 2
+            key = (str(device), m)
+            if key not in _EVAL_BUFFERS:
+                _EVAL_BUFFERS[key] = [torch.empty((m, 4), dtype=torch.int64, device=device) for _ in range(3)]
+            bufs = _EVAL_BUFFERS[key]
+            state = prove_begin(assignment, params, device_ptrs)
+    except Exception as e:
         msg = str(e)
         status = next((code for code, cls in _ERRORS.items() if isinstance(e, cls)), 17 if isinstance(e, BackendError) else 255)
-    world = dist.get_world_size(group)
-    backend = dist.get_backend(group)
-    device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    if split_h and world > 1:
+        # stage 1 of the polynomials this rank owns; a failure is carried to the all-gather, the broadcasts below
+        # are entered by every rank whatever happened (a collective nobody may skip)
+        if status == 0:
+            try:
+                for i, name in enumerate(("a", "b", "c")):
+                    if h_owner(i, world) == rank:
+                        if device_ptrs is not None:
+                            h_coset_evals(params.worker, device_ptrs[name], n, bufs[i].data_ptr(), on_device=True)
+                        else:
+                            h_coset_evals(params.worker, getattr(assignment, name), n, bufs[i].data_ptr())
+            except Exception as e:
+                msg = str(e)
+                status = next((code for code, cls in _ERRORS.items() if isinstance(e, cls)), 17 if isinstance(e, BackendError) else 255)
+        if state is None and status == 0:
+            status, msg = 255, "prove_begin returned no state"
+        if status != 0 and "bufs" not in locals():      # the buffers could not even be made: take part with scratch ones
+            bufs = [torch.empty((m if "m" in locals() else 1, 4), dtype=torch.int64, device=device) for _ in range(3)]
+        pending = [dist.broadcast(bufs[i], src=h_owner(i, world), group=group, async_op=True) for i in range(3)]
+        for p in pending:
+            p.wait()
+        if backend == "nccl":
+            torch.cuda.current_stream().synchronize()
+        try:
+            if state is not None:
+                if status == 0:
+                    blob = prove_end(state, [b.data_ptr() for b in bufs])
+                else:
+                    try:
+                        prove_end(state, None)           # drain and free what prove_begin queued
+                    except Exception:
+                        pass
+        except Exception as e:
+            msg = str(e)
+            status = next((code for code, cls in _ERRORS.items() if isinstance(e, cls)), 17 if isinstance(e, BackendError) else 255)
+    else:
+        try:
+            blob = prove_partials(assignment, params, device_ptrs)
+        except Exception as e:                           # whatever it is, the other ranks must not be left in the all-gather
+            msg = str(e)
+            status = next((code for code, cls in _ERRORS.items() if isinstance(e, cls)), 17 if isinstance(e, BackendError) else 255)
     # one collective: partial sums, status and (on failure) the failing rank's own message
     text = msg.encode("utf-8", "replace")[:MSG_BYTES].ljust(MSG_BYTES, b"\0")
     mine = torch.frombuffer(bytearray(blob + bytes([status]) + text), dtype=torch.uint8).to(device)
@@ -85,11 +151,11 @@ def create_proof_sharded(assignment, params, full_vk_params, r, s, device_ptrs=N
     gathered = [bytes(t.cpu().numpy()) for t in out]
     if worker_thread is not None:
         worker_thread.join()
-    for rank, g in enumerate(gathered):
+    for rk, g in enumerate(gathered):
         if g[PARTIALS_BYTES]:
             code = g[PARTIALS_BYTES]
             what = g[PARTIALS_BYTES + 1:].rstrip(b"\0").decode("utf-8", "replace")
-            raise _ERRORS.get(code, BackendError)(f"rank {rank} failed with status {code}" + (f": {what}" if what else ""))
-    if dist.get_rank(group) == 0:
+            raise _ERRORS.get(code, BackendError)(f"rank {rk} failed with status {code}" + (f": {what}" if what else ""))
+    if rank == 0:
         return finalize(full_vk_params, [g[:PARTIALS_BYTES] for g in gathered], r, s, static=ahead.get("static"))
     return None

@@ -58,6 +58,7 @@ typedef struct bb_ctx bb_ctx;         /* one CUDA device; stands where multicore
 typedef struct bb_bases bb_bases;     /* device-resident Arc<Vec<G::Affine>> (groth16/src/lib.rs:227-243) */
 typedef struct bb_msm_job bb_msm_job; /* Waiter<Result<G, SynthesisError>> (src/multicore.rs:94-118) */
 typedef struct bb_crs bb_crs;         /* device-resident groth16::Parameters (groth16/src/lib.rs:222-244) */
+typedef struct bb_prove bb_prove;     /* one create_proof in flight between bb_groth16_prove_begin and _end */
 
 const char* bb_last_error(void);
 int bb_version(void);
@@ -200,6 +201,20 @@ typedef struct bb_witness {
 #define BB_PARTIALS_BYTES 960
 /* NTT pipeline + the 8 MSMs over this context's CRS shard. */
 int bb_groth16_prove_partials(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, uint8_t partials[BB_PARTIALS_BYTES]);
+/* The same in two steps, for multi-GPU provers that split the H pipeline by polynomial.  _begin uploads the
+ * assignments and queues the seven witness MSMs (prover.rs:263-318) -- they need nothing from the H pipeline
+ * -- and returns at once.  Meanwhile each of a, b, c is taken through from_coeffs / ifft / coset_fft
+ * (prover.rs:225-230) by ONE rank with bb_h_coset_evals and the three result vectors (m Fr each, device
+ * memory) are broadcast (NCCL).  _end(state, evals_a, evals_b, evals_c, partials) then runs mul_assign /
+ * sub_assign / divide_by_z_on_coset / icoset_fft (:232-237) and the h MSM (:238-244), waits for all eight MSMs
+ * and frees the state; with three NULL pointers it runs the whole H pipeline from w->a, w->b, w->c itself.
+ * evals_a is clobbered.  The witness arrays must stay valid until _end returns. */
+int bb_groth16_prove_begin(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, bb_prove** out);
+int bb_groth16_prove_end(bb_prove* state, const void* d_evals_a, const void* d_evals_b, const void* d_evals_c,
+                         uint8_t partials[BB_PARTIALS_BYTES]);
+/* d_out[0..m) = coset_fft(ifft(from_coeffs(poly))) for one polynomial of n_constraints Fr (Montgomery; host
+ * memory, or device memory with on_device != 0); m = next power of two >= n_constraints.  Blocking. */
+int bb_h_coset_evals(bb_ctx* ctx, const void* poly, size_t n_constraints, int on_device, void* d_out);
 /* Sums `count` partial sets (one per shard) and applies prover.rs:320-360 + Proof::write
  * (groth16/src/lib.rs:39-45).  r, s: 32-byte canonical little-endian scalars. */
 int bb_groth16_finalize(const bb_crs* crs, const uint8_t* partials, size_t count,

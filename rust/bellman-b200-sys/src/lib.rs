@@ -9,6 +9,7 @@ use std::os::raw::{c_char, c_int, c_long, c_void};
 #[repr(C)] pub struct bb_bases { _private: [u8; 0] }
 #[repr(C)] pub struct bb_msm_job { _private: [u8; 0] }
 #[repr(C)] pub struct bb_crs { _private: [u8; 0] }
+#[repr(C)] pub struct bb_prove { _private: [u8; 0] }
 
 // bb_status
 pub const BB_OK: c_int = 0;
@@ -105,6 +106,10 @@ extern "C" {
     pub fn bb_crs_destroy(crs: *mut bb_crs);
 
     pub fn bb_groth16_prove_partials(ctx: *mut bb_ctx, crs: *const bb_crs, w: *const bb_witness, partials: *mut u8) -> c_int;
+    pub fn bb_groth16_prove_begin(ctx: *mut bb_ctx, crs: *const bb_crs, w: *const bb_witness, out: *mut *mut bb_prove) -> c_int;
+    pub fn bb_groth16_prove_end(state: *mut bb_prove, d_evals_a: *const c_void, d_evals_b: *const c_void, d_evals_c: *const c_void,
+                                partials: *mut u8) -> c_int;
+    pub fn bb_h_coset_evals(ctx: *mut bb_ctx, poly: *const c_void, n_constraints: usize, on_device: c_int, d_out: *mut c_void) -> c_int;
     pub fn bb_groth16_finalize(crs: *const bb_crs, partials: *const u8, count: usize, r: *const u8, s: *const u8,
                                proof: *mut u8) -> c_int;
     pub fn bb_groth16_finalize_static(crs: *const bb_crs, r: *const u8, s: *const u8, static_out: *mut u8) -> c_int;

@@ -49,7 +49,7 @@ WORKER = textwrap.dedent('''
         return bytes(bb.PARTIALS_BYTES)
     bb.prove_partials = fake_partials
     try:
-        D.create_proof_sharded(None, None, None, 1, 2)
+        D.create_proof_sharded(None, None, None, 1, 2, split_h=False)
         raise SystemExit("expected UnexpectedIdentity")
     except bb.UnexpectedIdentity as e:
         assert "rank 1" in str(e) and "identity in the CRS shard of rank 1" in str(e)   # the failing rank's own text, on every rank
@@ -91,11 +91,12 @@ SHARDED_PROVE = textwrap.dedent('''
     worker = bb.Worker(0)
     mine = bb.Parameters(worker, mc.export_params(), shard_index=rank, shard_count=world)
     r, s = rng.randrange(R), rng.randrange(R)
-    proof = create_proof_sharded(asg, mine, mine, r, s)
-    if rank == 0:
-        assert proof == mc.prove(r, s) == mc.expected_proof(r, s)
-    else:
-        assert proof is None
+    for split_h in (True, False):                 # H pipeline divided by polynomial across the ranks / replicated
+        proof = create_proof_sharded(asg, mine, mine, r, s, split_h=split_h)
+        if rank == 0:
+            assert proof == mc.prove(r, s) == mc.expected_proof(r, s), split_h
+        else:
+            assert proof is None
     # a shard with an identity base: every rank raises the same SynthesisError
     bad = mc.export_params()
     if rank == 1:
@@ -112,15 +113,17 @@ SHARDED_PROVE = textwrap.dedent('''
 ''')
 
 
-def test_sharded_prove_gloo_world2_emulated_device(tmp_path, emu_lib):
-    """The whole N>1 path on CPU: two gloo ranks, each running the product sources on host fibers
-    (tests/native) over its (base range x window) shard, one all-gather, finalize on rank 0 with
-    the static terms computed on a host thread meanwhile."""
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_prove_gloo_emulated_device(tmp_path, emu_lib, world):
+    """The whole N>1 path on CPU: gloo ranks, each running the product sources on host fibers
+    (tests/native) over its (base range x window) shard; the H pipeline split by polynomial (two ranks:
+    a, c | b; three: a | b | c) with broadcasts of the coset evaluations, and replicated; one all-gather,
+    finalize on rank 0 with the static terms computed on a host thread meanwhile."""
     script = tmp_path / "worker.py"
     script.write_text(SHARDED_PROVE)
     env = dict(os.environ, BB_ROOT=ROOT, BB_EMU_LIB=emu_lib)
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29519", str(script)]
-    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29519 + world), str(script)]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout + res.stderr
-    assert (tmp_path / "ok.0").exists() and (tmp_path / "ok.1").exists(), res.stdout + res.stderr
+    assert all((tmp_path / f"ok.{r}").exists() for r in range(world)), res.stdout + res.stderr
