@@ -23,4 +23,4 @@ except Exception as e:
 PY
 }
 for n in 2 4 8; do [ $n -le $NG ] && run p20_n$n $n --steps 10 --warmup 3; done
-for n in 1 2 4 8; do [ $n -le $NG ] && run p22_n$n $n --log-size 22 --steps 5 --warmup 2; done
+for n in 2 4 8; do [ $n -le $NG ] && run p22_n$n $n --log-size 22 --steps 5 --warmup 2; done
