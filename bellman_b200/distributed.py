@@ -43,6 +43,14 @@ def max_over_ranks(seconds, group=None):
 
 
 _EVAL_BUFFERS = {}       # (device, m) -> three tensors of m Fr: the coset evaluations of a, b, c on this rank
+HOST_MS = {}             # accumulated host milliseconds of create_proof_sharded's phases on this rank (bench.py reads and resets it)
+
+
+def _mark(name, t0):
+    import time
+    now = time.perf_counter()
+    HOST_MS[name] = HOST_MS.get(name, 0.0) + 1e3 * (now - t0)
+    return now
 
 
 def h_owner(poly_index, world):
@@ -86,10 +94,20 @@ def create_proof_sharded(assignment, params, full_vk_params, r, s, device_ptrs=N
                 ahead["error"] = e
         worker_thread = threading.Thread(target=_static)
         worker_thread.start()
+    import time
+    t_ = time.perf_counter()
     status, blob, msg = 0, bytes(PARTIALS_BYTES), ""
-    state = None
-    try:
-        if split_h and world > 1:
+
+    def code_of(e):
+        return next((code for code, cls in _ERRORS.items() if isinstance(e, cls)), 17 if isinstance(e, BackendError) else 255)
+
+    if split_h and world > 1:
+        # 1. the coset evaluations of the polynomials this rank owns -- the head of the longest chain, so it goes
+        #    first; 2. their broadcasts are enqueued (asynchronous); 3. the witness MSMs are queued underneath;
+        #    4. the broadcasts are awaited; 5. the last transform, the h MSM, the waits.  A failure is carried to
+        #    the all-gather; the broadcasts are entered by every rank whatever happened (nobody may skip a collective).
+        state, bufs, n = None, None, 0
+        try:
             n = assignment.a.shape[0]
             m = 1
             while m < n:
@@ -98,57 +116,53 @@ def create_proof_sharded(assignment, params, full_vk_params, r, s, device_ptrs=N
             if key not in _EVAL_BUFFERS:
                 _EVAL_BUFFERS[key] = [torch.empty((m, 4), dtype=torch.int64, device=device) for _ in range(3)]
             bufs = _EVAL_BUFFERS[key]
-            state = prove_begin(assignment, params, device_ptrs)
-    except Exception as e:
-        msg = str(e)
-        status = next((code for code, cls in _ERRORS.items() if isinstance(e, cls)), 17 if isinstance(e, BackendError) else 255)
-    if split_h and world > 1:
-        # stage 1 of the polynomials this rank owns; a failure is carried to the all-gather, the broadcasts below
-        # are entered by every rank whatever happened (a collective nobody may skip)
+            for i, name in enumerate(("a", "b", "c")):
+                if h_owner(i, world) == rank:
+                    if device_ptrs is not None:
+                        h_coset_evals(params.worker, device_ptrs[name], n, bufs[i].data_ptr(), on_device=True)
+                    else:
+                        h_coset_evals(params.worker, getattr(assignment, name), n, bufs[i].data_ptr())
+        except Exception as e:
+            msg, status = str(e), code_of(e)
+        if bufs is None:                                 # the buffers could not even be made: take part with scratch ones
+            bufs = [torch.empty((1, 4), dtype=torch.int64, device=device) for _ in range(3)]
+        t_ = _mark("h_stage1", t_)
+        pending = [dist.broadcast(bufs[i], src=h_owner(i, world), group=group, async_op=True) for i in range(3)]
         if status == 0:
             try:
-                for i, name in enumerate(("a", "b", "c")):
-                    if h_owner(i, world) == rank:
-                        if device_ptrs is not None:
-                            h_coset_evals(params.worker, device_ptrs[name], n, bufs[i].data_ptr(), on_device=True)
-                        else:
-                            h_coset_evals(params.worker, getattr(assignment, name), n, bufs[i].data_ptr())
+                state = prove_begin(assignment, params, device_ptrs)
             except Exception as e:
-                msg = str(e)
-                status = next((code for code, cls in _ERRORS.items() if isinstance(e, cls)), 17 if isinstance(e, BackendError) else 255)
-        if state is None and status == 0:
-            status, msg = 255, "prove_begin returned no state"
-        if status != 0 and "bufs" not in locals():      # the buffers could not even be made: take part with scratch ones
-            bufs = [torch.empty((m if "m" in locals() else 1, 4), dtype=torch.int64, device=device) for _ in range(3)]
-        pending = [dist.broadcast(bufs[i], src=h_owner(i, world), group=group, async_op=True) for i in range(3)]
+                msg, status = str(e), code_of(e)
+        t_ = _mark("queue_witness_msms", t_)
         for p in pending:
             p.wait()
         if backend == "nccl":
             torch.cuda.current_stream().synchronize()
-        try:
-            if state is not None:
+        t_ = _mark("broadcast_wait", t_)
+        if state is not None:
+            try:
                 if status == 0:
                     blob = prove_end(state, [b.data_ptr() for b in bufs])
                 else:
-                    try:
-                        prove_end(state, None)           # drain and free what prove_begin queued
-                    except Exception:
-                        pass
-        except Exception as e:
-            msg = str(e)
-            status = next((code for code, cls in _ERRORS.items() if isinstance(e, cls)), 17 if isinstance(e, BackendError) else 255)
+                    prove_end(state, None)               # drain and free what prove_begin queued
+            except Exception as e:
+                if status == 0:
+                    msg, status = str(e), code_of(e)
+        t_ = _mark("h_final_and_msm_waits", t_)
     else:
         try:
             blob = prove_partials(assignment, params, device_ptrs)
         except Exception as e:                           # whatever it is, the other ranks must not be left in the all-gather
-            msg = str(e)
-            status = next((code for code, cls in _ERRORS.items() if isinstance(e, cls)), 17 if isinstance(e, BackendError) else 255)
+            msg, status = str(e), code_of(e)
+        t_ = _mark("prove_partials", t_)
     # one collective: partial sums, status and (on failure) the failing rank's own message
     text = msg.encode("utf-8", "replace")[:MSG_BYTES].ljust(MSG_BYTES, b"\0")
     mine = torch.frombuffer(bytearray(blob + bytes([status]) + text), dtype=torch.uint8).to(device)
     out = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(out, mine, group=group)
-    gathered = [bytes(t.cpu().numpy()) for t in out]
+    gathered = bytes(torch.stack(out).cpu().numpy().tobytes())       # one device->host copy for all ranks' blobs
+    gathered = [gathered[i * len(mine):(i + 1) * len(mine)] for i in range(world)]
+    t_ = _mark("all_gather", t_)
     if worker_thread is not None:
         worker_thread.join()
     for rk, g in enumerate(gathered):
@@ -157,5 +171,7 @@ def create_proof_sharded(assignment, params, full_vk_params, r, s, device_ptrs=N
             what = g[PARTIALS_BYTES + 1:].rstrip(b"\0").decode("utf-8", "replace")
             raise _ERRORS.get(code, BackendError)(f"rank {rk} failed with status {code}" + (f": {what}" if what else ""))
     if rank == 0:
-        return finalize(full_vk_params, [g[:PARTIALS_BYTES] for g in gathered], r, s, static=ahead.get("static"))
+        proof = finalize(full_vk_params, [g[:PARTIALS_BYTES] for g in gathered], r, s, static=ahead.get("static"))
+        _mark("finalize", t_)
+        return proof
     return None

@@ -345,6 +345,9 @@ def run_prove(args):
             proof = step(device_ptrs)
         sync()
         worker.profile_reset()
+        if world > 1:
+            from bellman_b200 import distributed as _dm
+            _dm.HOST_MS.clear()
         l0 = worker.kernel_launches
         h0, d0 = worker.bytes_copied()
         t0 = time.perf_counter()
@@ -366,6 +369,8 @@ def run_prove(args):
     sampler.start()
     dt_val, proof_val, launches, _, _ = timed(dev, args.steps, args.warmup)
     clocks = sampler.stop()
+    from bellman_b200 import distributed as _dist_mod          # rank 0's host-side phases of the sharded prove (value leg)
+    host_ms = {k: round(v / args.steps, 3) for k, v in _dist_mod.HOST_MS.items()} if world > 1 else None
     acc_ms, acc_launches, acc_units = worker.profile_read("msm_accumulate_g1")
     tot_ms, _, _ = worker.profile_read("msm_total_g1")
     acc2_ms, acc2_launches, acc2_units = worker.profile_read("msm_accumulate_g2")
@@ -413,6 +418,7 @@ def run_prove(args):
                 "ms_per_step": 1e3 * dt_e2e / args.steps},
         "gpu_launches": int(launches),
         "proof_sha256": hashlib.sha256(proof_val).hexdigest() if rank == 0 else None,
+        "sharded_host_ms_per_step": host_ms,
         "proof_check": (None if rank else ("sharded proof == single-GPU proof of the same CRS/witness/r/s (192 bytes equal, rank 0)"
                                            if world > 1 else "value leg == e2e leg (192 bytes equal); parity with the oracle: tests/")),
         "clocks": clocks,
