@@ -102,10 +102,13 @@ def create_proof_sharded(assignment, params, full_vk_params, r, s, device_ptrs=N
         return next((code for code, cls in _ERRORS.items() if isinstance(e, cls)), 17 if isinstance(e, BackendError) else 255)
 
     if split_h and world > 1:
-        # 1. the coset evaluations of the polynomials this rank owns -- the head of the longest chain, so it goes
-        #    first; 2. their broadcasts are enqueued (asynchronous); 3. the witness MSMs are queued underneath;
-        #    4. the broadcasts are awaited; 5. the last transform, the h MSM, the waits.  A failure is carried to
-        #    the all-gather; the broadcasts are entered by every rank whatever happened (nobody may skip a collective).
+        # 1. the witness MSMs are queued (they need nothing from the H pipeline and keep the GPU busy from t = 0);
+        # 2. the coset evaluations of the polynomials this rank owns, on the high-priority stream; 3. their
+        # broadcasts; 4. the last transform, the h MSM, the waits.  Measured against "evaluations first, broadcasts
+        # enqueued before the witness MSMs": 13.0 / 13.5 / 22.0 ms against 15.9 / 16.6 / 24.5 ms at N = 8 / 4 / 2
+        # (profiles/multi_r02_*): the GPUs are work-bound, every millisecond without MSM kernels in flight is lost.
+        # A failure is carried to the all-gather; the broadcasts are entered by every rank whatever happened
+        # (nobody may skip a collective).
         state, bufs, n = None, None, 0
         try:
             n = assignment.a.shape[0]
@@ -116,24 +119,24 @@ def create_proof_sharded(assignment, params, full_vk_params, r, s, device_ptrs=N
             if key not in _EVAL_BUFFERS:
                 _EVAL_BUFFERS[key] = [torch.empty((m, 4), dtype=torch.int64, device=device) for _ in range(3)]
             bufs = _EVAL_BUFFERS[key]
-            for i, name in enumerate(("a", "b", "c")):
-                if h_owner(i, world) == rank:
-                    if device_ptrs is not None:
-                        h_coset_evals(params.worker, device_ptrs[name], n, bufs[i].data_ptr(), on_device=True)
-                    else:
-                        h_coset_evals(params.worker, getattr(assignment, name), n, bufs[i].data_ptr())
+            state = prove_begin(assignment, params, device_ptrs)
         except Exception as e:
             msg, status = str(e), code_of(e)
+        t_ = _mark("queue_witness_msms", t_)
+        if status == 0:
+            try:
+                for i, name in enumerate(("a", "b", "c")):
+                    if h_owner(i, world) == rank:
+                        if device_ptrs is not None:
+                            h_coset_evals(params.worker, device_ptrs[name], n, bufs[i].data_ptr(), on_device=True)
+                        else:
+                            h_coset_evals(params.worker, getattr(assignment, name), n, bufs[i].data_ptr())
+            except Exception as e:
+                msg, status = str(e), code_of(e)
         if bufs is None:                                 # the buffers could not even be made: take part with scratch ones
             bufs = [torch.empty((1, 4), dtype=torch.int64, device=device) for _ in range(3)]
         t_ = _mark("h_stage1", t_)
         pending = [dist.broadcast(bufs[i], src=h_owner(i, world), group=group, async_op=True) for i in range(3)]
-        if status == 0:
-            try:
-                state = prove_begin(assignment, params, device_ptrs)
-            except Exception as e:
-                msg, status = str(e), code_of(e)
-        t_ = _mark("queue_witness_msms", t_)
         for p in pending:
             p.wait()
         if backend == "nccl":
