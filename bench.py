@@ -76,7 +76,7 @@ def log(msg):
 def measured_traffic():
     """DRAM bytes per (base, scalar) pair of the dominant kernel from the committed ncu capture"""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "roofline_r01.json")))
+        d = json.load(open(os.path.join(ROOT, "profiles", "roofline_r02.json")))
         return float(d["traffic_bytes_per_pair"]), d["source"]
     except Exception:
         return None, None
