@@ -374,6 +374,9 @@ def run_prove(args):
     acc_ms, acc_launches, acc_units = worker.profile_read("msm_accumulate_g1")
     tot_ms, _, _ = worker.profile_read("msm_total_g1")
     acc2_ms, acc2_launches, acc2_units = worker.profile_read("msm_accumulate_g2")
+    ent_ms, _, ent_units = worker.profile_read("msm_entries_g1")
+    mul_ms, mul_rounds, mul_units = worker.profile_read("msm_fieldmuls_g1")
+    mul2_ms, _, mul2_units = worker.profile_read("msm_fieldmuls_g2")
     timeline = read_timeline(worker)
     worker.set_option("profile", 0)
     log(f"value leg done: {1e3 * dt_val / args.steps:.2f} ms/step; timed region: host buffers (e2e)")
@@ -398,9 +401,6 @@ def run_prove(args):
     # XYZZ kernel k_msm_accumulate), timed per job by CUDA events on the job's own stream.  Algorithmic bytes: 128 B
     # per (base, scalar) pair CONSUMED -- counted on the device by k_msm_digits: density-selected,
     # non-zero, in this rank's shard
-    ent_ms, _, ent_units = worker.profile_read("msm_entries_g1")
-    mul_ms, mul_rounds, mul_units = worker.profile_read("msm_fieldmuls_g1")
-    mul2_ms, _, mul2_units = worker.profile_read("msm_fieldmuls_g2")
     alg_bytes = 128.0 * acc_units
     achieved = alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None
     tr_pair, tr_src = measured_traffic()
