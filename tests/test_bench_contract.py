@@ -79,4 +79,5 @@ def test_own_arm_dry_run_on_the_emulated_device(tmp_path, emu_lib):
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
     assert {"value", "unit", "cores", "kind", "sample"} <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] == "port"
     assert len(d["timeline"]["device_ms_since_prove_start"]) == 8
+    assert d["roofline"]["pairs_per_step"] > 0 and d["roofline"]["bucket_entries_per_step"] > d["roofline"]["pairs_per_step"]
     assert "workload" in d["config"] and "model" not in d["config"]
