@@ -158,6 +158,15 @@ struct PairLoader {
 template <class F>
 __device__ __forceinline__ F ld_field(const F* p) { return ldg_words(p); }
 
+// resident CTAs per SM the phase kernels are compiled for (0 = whatever the registers allow).  G1 fits four
+// CTAs of 128 threads at 126-128 registers by itself; BB_AFF_G2_MINB caps the Fp2 instantiations (204
+// registers, two CTAs) for A/B runs.
+#ifndef BB_AFF_G2_MINB
+#define BB_AFF_G2_MINB 1
+#endif
+template <class F> struct AffBounds { static constexpr int MINB = 1; };
+template <> struct AffBounds<Fp2> { static constexpr int MINB = BB_AFF_G2_MINB; };
+
 // phase 1: denominators and their running products
 template <class F, bool GATHER>
 __global__ void __launch_bounds__(128) k_aff_phase1(PairLoader<F, GATHER> ld, const uint32_t* __restrict__ d_entries, uint32_t shift,
@@ -195,7 +204,7 @@ __global__ void __launch_bounds__(128) k_aff_phase1(PairLoader<F, GATHER> ld, co
 // thread's denominators).  err[1] is raised for an identity base selected by a digit (Source::next,
 // multiexp.rs:63-65) -- only gathered rows can be CRS bases.
 template <class F, bool GATHER>
-__global__ void __launch_bounds__(128) k_aff_phase3(PairLoader<F, GATHER> ld, const uint32_t* __restrict__ d_entries, uint32_t shift,
+__global__ void __launch_bounds__(128, AffBounds<F>::MINB) k_aff_phase3(PairLoader<F, GATHER> ld, const uint32_t* __restrict__ d_entries, uint32_t shift,
                                                     size_t T, uint32_t L, const F* __restrict__ pre, const F* __restrict__ tp,
                                                     Affine<F>* __restrict__ out, uint32_t* err) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

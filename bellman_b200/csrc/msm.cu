@@ -8,17 +8,18 @@
 //                     resolve the base index through the density map (:242-243, bases are
 //                     compacted to set bits), signed-digit recode into W windows (halves the
 //                     bucket count) and histogram the (window, |digit|) keys;
-//   2. scan           exclusive prefix sum of the histogram -> bucket segments;
+//   2. scan           exclusive prefix sum of the histogram, every count rounded up to a multiple
+//                     of 2^R -> padded bucket segments;
 //   3. k_msm_digits   again in scatter mode: counting sort of base indices by bucket;
-//   4. k_msm_accumulate  one thread per bucket: gather its affine bases from HBM (32 B
-//                     sector aligned, each read once per window) and sum them with XYZZ
-//                     mixed additions;
-//      (large MSMs first halve every bucket R times with batched-affine pairwise additions, 6 instead
-//      of 10 field multiplications per addition: batch_affine.cuh)
-//   5. k_msm_reduce   summation by parts per window, in parallel: every thread owns K
-//                     adjacent buckets (running-sum trick), lifts its partial by its bucket
-//                     offset with a short double-and-add, and the CTA tree-reduces;
-//   6. host           Horner fold of the W window sums (255 doublings), to_affine.
+//   4. halving rounds (batch_affine.cuh) x R: inside every bucket entries 0+1, 2+3, ... are added as
+//                     AFFINE points; all additions of a round share one inversion (Montgomery's
+//                     trick), 6 instead of 10 field multiplications each; R follows the mean fill;
+//   5. k_msm_accumulate  one thread per bucket sums what is left (all entries when R = 0) with
+//                     XYZZ mixed additions; oversized buckets are cut into tasks;
+//   6. bucket reduction  summation by parts (:271-275) in two dimensions (k_bucket_fold: row and
+//                     column sums as full-grid trees), then the serial running-sum recursion
+//                     (k_msm_reduce_level) only over 2 sqrt(D) entries per window;
+//   7. host           Horner fold of the W window sums (255 doublings), to_affine.
 // Scalars equal to one (Exponent::One, :246-252) bypass the buckets through a list that is
 // summed by a tree, zero scalars (Exponent::Zero, :245) are dropped -- exactly the
 // reference's fast paths, kept because real witnesses are dominated by 0/1.
