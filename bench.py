@@ -436,7 +436,7 @@ def run_prove(args):
                      "integer_roofline": {"bound": "int32 multiplier", "unit": "G Fp-mul/s",
                                           "achieved": (mul_units / (acc_ms * 1e-3) / 1e9) if acc_ms > 0 else None,
                                           "achieved_g2_in_fp_mul": (3.0 * mul2_units / (acc2_ms * 1e-3) / 1e9) if acc2_ms > 0 else None,
-                                          "whole_step": ((mul_units + 3.0 * mul2_units) / max(world, 1) / (dt_val * 1e9)) if dt_val else None,
+                                          "whole_step": ((mul_units + 3.0 * mul2_units) / (dt_val * 1e9)) if dt_val else None,
                                           "peak": 31.2, "peak_source": "profiles/ubench_r01.txt: 288 IMAD.WIDE-class products per Fp-mul at ~30/clk/SM",
                                           "note": "`achieved` is one job's stage rate while ~5 jobs share the machine; `whole_step` = all accumulation-stage "
                                                   "multiplications of the step (G2 counted as 3 Fp each) over the step's wall time; the dominant kernel alone "
