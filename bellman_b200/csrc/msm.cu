@@ -552,6 +552,7 @@ struct bb_msm_job {
     void* h_out = nullptr;           // pinned: [W window sums][1 ones sum] then err[4]
     size_t h_out_bytes = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // profile: job start, accumulate start/end, job end
+    cudaEvent_t ev_done = nullptr;   // blocking-sync event behind the result copy: the waiting host thread sleeps instead of spinning
 };
 
 namespace {
@@ -1076,6 +1077,12 @@ int launch_msm(bb_msm_job* job) {
     BB_CUDA(cudaMemcpyAsync((char*)job->h_out + pts, job->d_err.p, 32, cudaMemcpyDeviceToHost, st));
     ctx->d2h_bytes += pts + 32;
     if (prof) BB_CUDA(cudaEventRecord(job->ev[3], st));
+    // a proof has eight of these waits on eight host threads, and a multi-GPU box one process per GPU: the waiters
+    // must not burn a core each (cudaStreamSynchronize spins by default)
+    if (cudaEventCreateWithFlags(&job->ev_done, cudaEventBlockingSync | cudaEventDisableTiming) == cudaSuccess) {
+        if (cudaEventRecord(job->ev_done, st) != cudaSuccess) { cudaEventDestroy(job->ev_done); job->ev_done = nullptr; }
+    } else job->ev_done = nullptr;
+    cudaGetLastError();
     return BB_OK;
 }
 
@@ -1249,7 +1256,8 @@ namespace bb {
 int msm_wait_result(bb_msm_job* job, MsmResult* res) {
     int status = job->status;
     {   // also on a failed launch: kernels already queued may still use the job's buffers
-        cudaError_t e = cudaStreamSynchronize(job->st);
+        if (job->ev_done) { cudaEventSynchronize(job->ev_done); cudaEventDestroy(job->ev_done); job->ev_done = nullptr; }   // sleeps
+        cudaError_t e = cudaStreamSynchronize(job->st);                                                                     // returns at once after that
         if (e != cudaSuccess && status == BB_OK) { set_error("msm stream: %s", cudaGetErrorString(e)); status = BB_ERR_CUDA; }
     }
     if (status == BB_OK) {
