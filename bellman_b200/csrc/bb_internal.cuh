@@ -56,7 +56,8 @@ struct bb_ctx {
     long opt_ntt_radix8 = 0;          // 1 = register radix-8 windows (k_ntt_pass8); measured 4-5 % slower than the radix-2 sweeps on B200
                                       // (2^24 fwd+inv 9.74 vs 9.34 ms, profiles/ab_r02_call4.txt), so it stays an option
     long opt_profile = 0;
-    long opt_msm_acc_variant = 0;
+    long opt_msm_acc_variant = 0;     // accepted and ignored: the launch-bound / prefetch variants of round 1's accumulate kernel
+                                      // measured no gain (profiles/ab_r02_call1...) and were removed
     long opt_msm_reduce_2d = 1;      // bucket reduction through row / column sums (k_bucket_fold) for windows of >= 1024 buckets
     long opt_msm_reduce_k = 4;       // entries per thread and level of the bucket reduction: 4 halves the length of the
     long opt_msm_reduce_k1 = 4;      // dependent-addition chain of 16 (2K per level, log_K D levels) for 1.25x its additions

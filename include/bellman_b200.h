@@ -68,9 +68,18 @@ int bb_version(void);
  * BB_ERR_NO_DEVICE when no CUDA device is usable: there is no CPU fallback. */
 int bb_ctx_create(int device, bb_ctx** out);
 void bb_ctx_destroy(bb_ctx* ctx);
-/* tuning knobs; results never depend on them.  Known keys: "msm_window_bits" (0 = auto),
- * "msm_precompute" (1 = keep window multiples of every base vector resident, see
- * bb_bases_precompute), "ntt_tile_log" , "ntt_col_bits". */
+/* tuning knobs; results never depend on them.  Keys:
+ *   msm_window_bits    window size c of the signed-digit Pippenger (0 = by size)
+ *   msm_affine_rounds  batched-affine halving rounds before the XYZZ stage (-1 = by mean bucket fill, 0 = none)
+ *   msm_affine_batch   pairs per thread in those rounds (default 16)
+ *   msm_affine_tma     1 = dense rounds of G1 jobs staged by cp.async.bulk + mbarrier (default 0: measured neutral)
+ *   msm_reduce_2d      0 = bucket reduction by the serial recursion over whole windows (default 1: row/column sums first)
+ *   msm_reduce_k, msm_reduce_k1   entries per thread of the serial recursion (powers of two, default 4)
+ *   msm_big_cap        bucket size above which a bucket is cut into tasks (0 = by mean fill)
+ *   msm_precompute     1 = keep window multiples of every base vector resident (see bb_bases_precompute)
+ *   shard_windows      multi-GPU: window groups per base range (default 4; 1 = base ranges only)
+ *   ntt_radix8         1 = register radix-8 NTT windows (default 0: measured slower), ntt_tile_log, ntt_col_bits
+ *   profile            1 = CUDA-event timing of the MSM stages (bb_profile_read) */
 int bb_ctx_set_option(bb_ctx* ctx, const char* key, long value);
 int bb_ctx_synchronize(bb_ctx* ctx);
 /* counters for the harness: number of kernels this context has launched */
