@@ -512,11 +512,16 @@ def prove_begin(assignment, params, device_ptrs=None):
     return h
 
 
+def _addr(p):
+    """device address as an int, from an int or a ctypes void pointer (Worker.device_alloc returns the latter)"""
+    return p.value if isinstance(p, C.c_void_p) else int(p)
+
+
 def prove_end(state, evals=None):
     """bb_groth16_prove_end: `evals` = device addresses of the coset evaluations of a, b, c (bb_h_coset_evals on
     whichever rank computed them), or None to run the whole H pipeline here -> 960 bytes of partial sums."""
     out = (C.c_uint8 * PARTIALS_BYTES)()
-    ea, eb, ec = (C.c_void_p(p) for p in evals) if evals is not None else (None, None, None)
+    ea, eb, ec = (C.c_void_p(_addr(p)) for p in evals) if evals is not None else (None, None, None)
     _check(load_library().bb_groth16_prove_end(state, ea, eb, ec, out))
     return bytes(out)
 
@@ -524,8 +529,8 @@ def prove_end(state, evals=None):
 def h_coset_evals(worker, poly, n_constraints, d_out, on_device=False):
     """coset_fft(ifft(from_coeffs(poly))) of ONE of a, b, c (prover.rs:225-230) into the device buffer d_out
     (m Fr).  `poly`: numpy array (host) or a device address with on_device=True."""
-    src = C.c_void_p(poly) if on_device else _ptr(poly)
-    _check(load_library().bb_h_coset_evals(worker._h, src, C.c_size_t(n_constraints), C.c_int(1 if on_device else 0), C.c_void_p(d_out)))
+    src = C.c_void_p(_addr(poly)) if on_device else _ptr(poly)
+    _check(load_library().bb_h_coset_evals(worker._h, src, C.c_size_t(n_constraints), C.c_int(1 if on_device else 0), C.c_void_p(_addr(d_out))))
 
 
 PROOF_STATIC_BYTES = 768

@@ -319,3 +319,7 @@ def test_emulated_pipeline_over_the_host_arithmetic_path(tmp_path):
         w.close()
     finally:
         bb.LIB_PATH, bb._lib = saved
+
+
+def test_emulated_prove_begin_end(worker):
+    G.test_prove_begin_end_with_coset_evaluations(worker)

@@ -876,3 +876,35 @@ def test_precompute_prove(precompute):
     test_prove_mimc322_matches_oracle(precompute)
     test_prove_synthetic_chain_trapdoor(precompute, 8191)
     test_prove_error_precedence(precompute)
+
+
+def test_prove_begin_end_with_coset_evaluations(worker):
+    """The two-step prove of the multi-GPU flow on one device: bb_groth16_prove_begin queues the witness MSMs,
+    bb_h_coset_evals takes a, b, c through ifft + coset_fft one by one (as three ranks would), and
+    bb_groth16_prove_end finishes with the last transform and the h MSM.  Same 960 partial-sum bytes and the same
+    proof as the one-call path; also with the H pipeline left to prove_end (no evaluations passed)."""
+    rng = random.Random(44)
+    mc = o1.Mimc(100, seed=45)
+    mc.set_toxic([rng.randrange(1, R) for _ in range(5)])
+    mc.generate()
+    params = bb.Parameters(worker, mc.export_params())
+    asg = _assignment(mc.witness())
+    r, s = rng.randrange(R), rng.randrange(R)
+    want = bb.prove_partials(asg, params)
+    n = asg.a.shape[0]
+    m = 1
+    while m < n:
+        m *= 2
+    bufs = [worker.device_alloc(m * 32) for _ in range(3)]
+    try:
+        state = bb.prove_begin(asg, params)
+        for poly, d in zip((asg.a, asg.b, asg.c), bufs):
+            bb.h_coset_evals(worker, poly, n, d)
+        got = bb.prove_end(state, bufs)
+        assert got == want
+        assert bb.finalize(params, [got], r, s) == mc.prove(r, s) == mc.expected_proof(r, s)
+        state = bb.prove_begin(asg, params)
+        assert bb.prove_end(state, None) == want
+    finally:
+        for d in bufs:
+            worker.device_free(d)
