@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(128, AffBounds<F>::MINB) k_aff_phase3(PairLoad
         Affine<F> P1 = n1 ? Affine<F>::identity() : ld_affine(r1);
         Affine<F> P2 = n2 ? Affine<F>::identity() : ld_affine(r2);
         bool i1 = affine_is_identity(P1), i2 = affine_is_identity(P2);
-        if (GATHER && ((i1 && !n1) || (i2 && !n2))) err[1] = 1;
+        if (GATHER && ((i1 && !n1) || (i2 && !n2))) atomicOr(&err[1], 1u);
         if (g1) P1.y = P1.y.neg();
         if (g2) P2.y = P2.y.neg();
         if (i1 || i2) { st_words(out + j, i1 ? P2 : P1); continue; }

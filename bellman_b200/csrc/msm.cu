@@ -250,7 +250,7 @@ __device__ __forceinline__ XYZZ<F> accumulate_range(const Affine<F>* __restrict_
         } else {
             uint32_t v = sorted[k];
             Affine<F> p = ld_affine(bases + (v & 0x7fffffffu));
-            if (p.is_identity()) { err[1] = 1; continue; }           // Source::next, multiexp.rs:63-65
+            if (p.is_identity()) { atomicOr(&err[1], 1u); continue; }           // Source::next, multiexp.rs:63-65
             if (v >> 31) p.y = p.y.neg();
             acc.add_mixed(p);
         }
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(128) k_msm_sum_list(const Affine<F>* __restric
     XYZZ<F> acc = XYZZ<F>::identity();
     for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
         Affine<F> p = ld_affine(bases + list[k]);
-        if (p.is_identity()) { err[1] = 1; continue; }
+        if (p.is_identity()) { atomicOr(&err[1], 1u); continue; }
         acc.add_mixed(p);
     }
     block_tree_reduce(acc, sh);

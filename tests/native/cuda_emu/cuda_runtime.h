@@ -283,6 +283,7 @@ inline unsigned __shfl_up_sync(unsigned, unsigned v, unsigned d) {
     return r;
 }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned atomicMin(unsigned* p, unsigned v) {
     unsigned old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
     while (old > v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
