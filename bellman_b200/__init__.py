@@ -526,6 +526,17 @@ def prove_end(state, evals=None):
     return bytes(out)
 
 
+def h_coset_evals_async(worker, poly, n_constraints, d_out, on_device=False):
+    """bb_h_coset_evals_async: queue the upload and the two transforms of one polynomial, return at once; the
+    caller keeps `poly` and the output buffer alive until h_coset_evals_wait(worker)."""
+    src = C.c_void_p(_addr(poly)) if on_device else _ptr(poly)
+    _check(load_library().bb_h_coset_evals_async(worker._h, src, C.c_size_t(n_constraints), C.c_int(1 if on_device else 0), C.c_void_p(_addr(d_out))))
+
+
+def h_coset_evals_wait(worker):
+    _check(load_library().bb_h_coset_evals_wait(worker._h))
+
+
 def h_coset_evals(worker, poly, n_constraints, d_out, on_device=False):
     """coset_fft(ifft(from_coeffs(poly))) of ONE of a, b, c (prover.rs:225-230) into the device buffer d_out
     (m Fr).  `poly`: numpy array (host) or a device address with on_device=True."""

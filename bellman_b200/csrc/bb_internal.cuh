@@ -75,6 +75,7 @@ struct bb_ctx {
         e.ms += ms; e.launches += launches; e.units += units;
     }
     std::map<uint32_t, bb::NttTables*> ntt_tables;   // by log_n
+    std::vector<void*> h_evals_scratch;              // transform scratch of bb_h_coset_evals_async calls not yet waited for
     cudaEvent_t epoch_ev = nullptr;                  // profile mode: start of the current prove (device timeline origin)
 
     // small page-locked staging blocks for results (cudaMallocHost/cudaFreeHost synchronise the

@@ -452,8 +452,9 @@ int bb_groth16_prove_end(bb_prove* state, const void* d_evals_a, const void* d_e
 }
 
 // from_coeffs (zero padding to m), ifft and coset_fft of ONE of the polynomials a, b, c (prover.rs:225-230) into a
-// device buffer of m Fr; returns when the result is there
-int bb_h_coset_evals(bb_ctx* ctx, const void* poly, size_t n_constraints, int on_device, void* d_out) {
+// device buffer of m Fr.  _async queues the copy and the two transforms on the high-priority stream and returns;
+// _wait blocks until every queued evaluation is there (and hands the scratch buffers back).
+int bb_h_coset_evals_async(bb_ctx* ctx, const void* poly, size_t n_constraints, int on_device, void* d_out) {
     if (!ctx || !d_out || (n_constraints && !poly)) { set_error("bb_h_coset_evals: null argument"); return BB_ERR_ARG; }
     BB_CUDA(cudaSetDevice(ctx->device));
     size_t m = 1;
@@ -464,15 +465,36 @@ int bb_h_coset_evals(bb_ctx* ctx, const void* poly, size_t n_constraints, int on
         if (log_m >= (uint32_t)bbc::FR_S) { set_error("PolynomialDegreeTooLarge"); return BB_ERR_POLYNOMIAL_DEGREE_TOO_LARGE; }
     }
     cudaStream_t st = ctx->main_stream;
-    DevBuf d_tmp;
-    BB_TRY(d_tmp.alloc(ctx, m * 32));
+    void* d_tmp = nullptr;
+    BB_TRY(ctx->alloc(m * 32, &d_tmp));
+    {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        ctx->h_evals_scratch.push_back(d_tmp);            // released by bb_h_coset_evals_wait, after the stream has drained
+    }
     if (m > n_constraints) BB_CUDA(cudaMemsetAsync((char*)d_out + n_constraints * 32, 0, (m - n_constraints) * 32, st));
     if (n_constraints) BB_CUDA(cudaMemcpyAsync(d_out, poly, n_constraints * 32, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     if (!on_device) ctx->h2d_bytes += n_constraints * 32;
-    int s = h_poly_evals_device(ctx, st, (Fr*)d_out, d_tmp.as<Fr>(), log_m);
-    cudaError_t e = cudaStreamSynchronize(st);
-    if (s == BB_OK && e != cudaSuccess) { set_error("bb_h_coset_evals: %s", cudaGetErrorString(e)); s = BB_ERR_CUDA; }
-    return s;
+    return h_poly_evals_device(ctx, st, (Fr*)d_out, (Fr*)d_tmp, log_m);
+}
+
+int bb_h_coset_evals_wait(bb_ctx* ctx) {
+    if (!ctx) { set_error("bb_h_coset_evals_wait: null argument"); return BB_ERR_ARG; }
+    BB_CUDA(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaStreamSynchronize(ctx->main_stream);
+    std::vector<void*> scratch;
+    {
+        std::lock_guard<std::mutex> g(ctx->mu);
+        scratch.swap(ctx->h_evals_scratch);
+    }
+    for (void* p : scratch) ctx->release(p);
+    if (e != cudaSuccess) { set_error("bb_h_coset_evals: %s", cudaGetErrorString(e)); return BB_ERR_CUDA; }
+    return BB_OK;
+}
+
+int bb_h_coset_evals(bb_ctx* ctx, const void* poly, size_t n_constraints, int on_device, void* d_out) {
+    int s = bb_h_coset_evals_async(ctx, poly, n_constraints, on_device, d_out);
+    int w = ctx ? bb_h_coset_evals_wait(ctx) : BB_OK;
+    return s != BB_OK ? s : w;
 }
 
 int bb_groth16_finalize(const bb_crs* crs, const uint8_t* partials, size_t count, const uint8_t* r_bytes, const uint8_t* s_bytes,

@@ -77,7 +77,7 @@ def create_proof_sharded(assignment, params, full_vk_params, r, s, device_ptrs=N
 
     import threading
 
-    from . import BackendError, _ERRORS, finalize, finalize_static, h_coset_evals, prove_begin, prove_end, prove_partials
+    from . import BackendError, _ERRORS, finalize, finalize_static, h_coset_evals_async, h_coset_evals_wait, prove_begin, prove_end, prove_partials
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     backend = dist.get_backend(group)
@@ -102,14 +102,18 @@ def create_proof_sharded(assignment, params, full_vk_params, r, s, device_ptrs=N
         return next((code for code, cls in _ERRORS.items() if isinstance(e, cls)), 17 if isinstance(e, BackendError) else 255)
 
     if split_h and world > 1:
-        # 1. the witness MSMs are queued (they need nothing from the H pipeline and keep the GPU busy from t = 0);
-        # 2. the coset evaluations of the polynomials this rank owns, on the high-priority stream; 3. their
-        # broadcasts; 4. the last transform, the h MSM, the waits.  Measured against "evaluations first, broadcasts
-        # enqueued before the witness MSMs": 13.0 / 13.5 / 22.0 ms against 15.9 / 16.6 / 24.5 ms at N = 8 / 4 / 2
-        # (profiles/multi_r02_*): the GPUs are work-bound, every millisecond without MSM kernels in flight is lost.
+        # 1. the coset evaluations of the polynomials this rank owns are LAUNCHED (asynchronous, high-priority stream):
+        #    they head the longest chain of the proof; 2. the witness MSMs are queued underneath (~1 ms of host time,
+        #    during which the transforms already run); 3. the evaluations are awaited and broadcast; 4. the last
+        #    transform, the h MSM, the waits.  Measured variants (profiles/multi_r02_*): with the evaluations computed
+        #    and AWAITED before the witness MSMs were queued, and the broadcasts enqueued under that queueing, the proof
+        #    took 15.9 / 16.6 / 24.5 ms at N = 8 / 4 / 2 against 12.9 / 13.6 / 22.0 ms with the witness MSMs queued
+        #    first and the evaluations (blocking) after -- the GPUs are work-bound, a millisecond without MSM kernels
+        #    in flight is lost; launching the transforms first without waiting for them keeps both properties.
         # A failure is carried to the all-gather; the broadcasts are entered by every rank whatever happened
         # (nobody may skip a collective).
         state, bufs, n = None, None, 0
+        launched = False
         try:
             n = assignment.a.shape[0]
             m = 1
@@ -119,23 +123,31 @@ def create_proof_sharded(assignment, params, full_vk_params, r, s, device_ptrs=N
             if key not in _EVAL_BUFFERS:
                 _EVAL_BUFFERS[key] = [torch.empty((m, 4), dtype=torch.int64, device=device) for _ in range(3)]
             bufs = _EVAL_BUFFERS[key]
-            state = prove_begin(assignment, params, device_ptrs)
+            launched = True
+            for i, name in enumerate(("a", "b", "c")):
+                if h_owner(i, world) == rank:
+                    if device_ptrs is not None:
+                        h_coset_evals_async(params.worker, device_ptrs[name], n, bufs[i].data_ptr(), on_device=True)
+                    else:
+                        h_coset_evals_async(params.worker, getattr(assignment, name), n, bufs[i].data_ptr())
         except Exception as e:
             msg, status = str(e), code_of(e)
-        t_ = _mark("queue_witness_msms", t_)
+        t_ = _mark("h_stage1_launch", t_)
         if status == 0:
             try:
-                for i, name in enumerate(("a", "b", "c")):
-                    if h_owner(i, world) == rank:
-                        if device_ptrs is not None:
-                            h_coset_evals(params.worker, device_ptrs[name], n, bufs[i].data_ptr(), on_device=True)
-                        else:
-                            h_coset_evals(params.worker, getattr(assignment, name), n, bufs[i].data_ptr())
+                state = prove_begin(assignment, params, device_ptrs)
             except Exception as e:
                 msg, status = str(e), code_of(e)
+        t_ = _mark("queue_witness_msms", t_)
+        if launched:
+            try:
+                h_coset_evals_wait(params.worker)
+            except Exception as e:
+                if status == 0:
+                    msg, status = str(e), code_of(e)
         if bufs is None:                                 # the buffers could not even be made: take part with scratch ones
             bufs = [torch.empty((1, 4), dtype=torch.int64, device=device) for _ in range(3)]
-        t_ = _mark("h_stage1", t_)
+        t_ = _mark("h_stage1_wait", t_)
         pending = [dist.broadcast(bufs[i], src=h_owner(i, world), group=group, async_op=True) for i in range(3)]
         for p in pending:
             p.wait()

@@ -212,7 +212,7 @@ typedef struct bb_witness {
 int bb_groth16_prove_partials(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, uint8_t partials[BB_PARTIALS_BYTES]);
 /* The same in two steps, for multi-GPU provers that split the H pipeline by polynomial.  _begin uploads the
  * assignments and queues the seven witness MSMs (prover.rs:263-318) -- they need nothing from the H pipeline
- * -- and returns at once.  Meanwhile each of a, b, c is taken through from_coeffs / ifft / coset_fft
+ * -- and returns at once.  Each of a, b, c is taken through from_coeffs / ifft / coset_fft
  * (prover.rs:225-230) by ONE rank with bb_h_coset_evals and the three result vectors (m Fr each, device
  * memory) are broadcast (NCCL).  _end(state, evals_a, evals_b, evals_c, partials) then runs mul_assign /
  * sub_assign / divide_by_z_on_coset / icoset_fft (:232-237) and the h MSM (:238-244), waits for all eight MSMs
@@ -224,6 +224,12 @@ int bb_groth16_prove_end(bb_prove* state, const void* d_evals_a, const void* d_e
 /* d_out[0..m) = coset_fft(ifft(from_coeffs(poly))) for one polynomial of n_constraints Fr (Montgomery; host
  * memory, or device memory with on_device != 0); m = next power of two >= n_constraints.  Blocking. */
 int bb_h_coset_evals(bb_ctx* ctx, const void* poly, size_t n_constraints, int on_device, void* d_out);
+/* The same without blocking: _async queues the copy and the two transforms on the context's high-priority stream
+ * and returns at once (poly and d_out must stay valid); _wait blocks until every evaluation queued so far is
+ * complete.  Lets a rank launch its transforms FIRST and queue the witness MSMs (bb_groth16_prove_begin, ~1 ms of
+ * host time) while they run. */
+int bb_h_coset_evals_async(bb_ctx* ctx, const void* poly, size_t n_constraints, int on_device, void* d_out);
+int bb_h_coset_evals_wait(bb_ctx* ctx);
 /* Sums `count` partial sets (one per shard) and applies prover.rs:320-360 + Proof::write
  * (groth16/src/lib.rs:39-45).  r, s: 32-byte canonical little-endian scalars. */
 int bb_groth16_finalize(const bb_crs* crs, const uint8_t* partials, size_t count,

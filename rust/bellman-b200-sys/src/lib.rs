@@ -110,6 +110,8 @@ extern "C" {
     pub fn bb_groth16_prove_end(state: *mut bb_prove, d_evals_a: *const c_void, d_evals_b: *const c_void, d_evals_c: *const c_void,
                                 partials: *mut u8) -> c_int;
     pub fn bb_h_coset_evals(ctx: *mut bb_ctx, poly: *const c_void, n_constraints: usize, on_device: c_int, d_out: *mut c_void) -> c_int;
+    pub fn bb_h_coset_evals_async(ctx: *mut bb_ctx, poly: *const c_void, n_constraints: usize, on_device: c_int, d_out: *mut c_void) -> c_int;
+    pub fn bb_h_coset_evals_wait(ctx: *mut bb_ctx) -> c_int;
     pub fn bb_groth16_finalize(crs: *const bb_crs, partials: *const u8, count: usize, r: *const u8, s: *const u8,
                                proof: *mut u8) -> c_int;
     pub fn bb_groth16_finalize_static(crs: *const bb_crs, r: *const u8, s: *const u8, static_out: *mut u8) -> c_int;
