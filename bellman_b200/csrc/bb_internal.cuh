@@ -13,6 +13,22 @@
 #include "../../include/bellman_b200_diag.h"
 #include "curve.cuh"
 
+// NVTX ranges (header-only nvtx3, no link dependency; a no-op unless a tool such as nsys is attached):
+// one range per prove, per MSM job launch sequence and per H pipeline, so that a timeline shows the job graph.
+#if defined(__CUDACC__)
+#include <nvtx3/nvToolsExt.h>
+namespace bb {
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace bb
+#else
+namespace bb {
+struct NvtxRange { explicit NvtxRange(const char*) {} };
+}  // namespace bb
+#endif
+
 namespace bb {
 
 void set_error(const char* fmt, ...);

@@ -898,6 +898,7 @@ uint32_t choose_affine_rounds(const bb_ctx* ctx, size_t pairs, uint64_t entries,
 
 template <class F>
 int launch_msm(bb_msm_job* job) {
+    NvtxRange range(job->tag ? job->tag : "bb: msm job");
     bb_ctx* ctx = job->ctx;
     cudaStream_t st = job->st;
     const uint32_t W = job->W_local, D = job->D;   // everything below works on the owned windows only

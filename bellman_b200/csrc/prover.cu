@@ -230,6 +230,7 @@ void prove_start_job(bb_prove* P, int slot, const bb_bases* bases, size_t off, c
 // (device buffers of m coset evaluations of a, b, c -- computed elsewhere, bb_h_coset_evals) only the last
 // transform remains: mul_assign, sub_assign, divide_by_z_on_coset, icoset_fft (:232-237).
 int prove_queue_h(bb_prove* P, const void* const* evals) {
+    NvtxRange range(evals ? "bb: H pipeline (last transform) + h MSM" : "bb: H pipeline + h MSM");
     bb_ctx* ctx = P->ctx;
     cudaStream_t st = ctx->main_stream;
     const bb_witness* w = &P->w;
@@ -260,6 +261,7 @@ int prove_queue_h(bb_prove* P, const void* const* evals) {
 // seven witness MSMs fill the machine around them.  Otherwise prove_end queues them (multi-GPU: the coset
 // evaluations arrive from other ranks while the witness MSMs already run).
 int prove_begin_impl(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, bool h_inline, bb_prove** out) {
+    NvtxRange range("bb: prove_begin (uploads, queue MSMs)");
     if (!ctx || !crs || !w || !out) { set_error("bb_groth16_prove: null argument"); return BB_ERR_ARG; }
     BB_CUDA(cudaSetDevice(ctx->device));
     const size_t n = w->n_constraints;
@@ -314,6 +316,7 @@ int prove_begin_impl(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, bool h
 // Frees the state.  `while_device_runs`, if given, is called once everything is queued and before the first
 // wait: host work that needs no MSM result goes there and overlaps the device.
 int prove_end_impl(bb_prove* Praw, const void* const* evals, uint8_t* partials, const std::function<void()>* while_device_runs) {
+    NvtxRange range("bb: prove_end (waits, folds)");
     std::unique_ptr<bb_prove> P(Praw);
     if (!Praw || !partials) { set_error("bb_groth16_prove_end: null argument"); return BB_ERR_ARG; }
     bb_ctx* ctx = P->ctx;
