@@ -429,8 +429,8 @@ def run_prove(args):
                      "launches": int(acc_launches), "avg_launch_ms": acc_ms / acc_launches if acc_launches else None,
                      "algorithmic_bytes_per_pair": 128,
                      "share_of_step": acc_ms / (1e3 * dt_val) if dt_val else None,
-                     "share_note": "sum of this kernel's launch durations (CUDA events on each job's stream) over the step time; "
-                                   "its launches overlap other streams' kernels, so the sum can approach or exceed the step",
+                     "share_note": "sum over the G1 jobs of the stage's duration (CUDA events on each job's own stream) over the step time; "
+                                   "the jobs overlap each other on different streams, so the sum can exceed the step",
                      "note": "integer-ALU bound, not HBM bound (SURVEY.md 8d): see integer_roofline",
                      "pairs_per_step": acc_units / args.steps, "bucket_entries_per_step": ent_units / args.steps,
                      "integer_roofline": {"bound": "int32 multiplier", "unit": "G Fp-mul/s",
