@@ -81,3 +81,33 @@ def test_own_arm_dry_run_on_the_emulated_device(tmp_path, emu_lib):
     assert len(d["timeline"]["device_ms_since_prove_start"]) == 8
     assert d["roofline"]["pairs_per_step"] > 0 and d["roofline"]["bucket_entries_per_step"] > d["roofline"]["pairs_per_step"]
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_sizes_its_pool_to_the_cpu_quota(monkeypatch):
+    """host_cpu_info(): threads = min(affinity, ceil(cgroup quota)) -- the 1-GPU lease of round 1 reported 128
+    cores under a 16-CPU quota (cpu.max = "1600000 100000"), and a 128-thread pool ran 3x slower than 16."""
+    import builtins
+    import importlib.util
+    import io
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    real_open = builtins.open
+
+    def fake_open(path, *a, **k):
+        if path == "/sys/fs/cgroup/cpu.max":
+            return io.StringIO(fake_open.content)
+        return real_open(path, *a, **k)
+
+    monkeypatch.setattr(builtins, "open", fake_open)
+    monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(128)), raising=False)
+    monkeypatch.delenv("BB_ORACLE_THREADS", raising=False)
+    fake_open.content = "1600000 100000\n"
+    info = bench.host_cpu_info()
+    assert info["threads"] == 16 and info["cgroup_quota_cpus"] == 16.0 and info["affinity"] == 128
+    fake_open.content = "max 100000\n"
+    assert bench.host_cpu_info()["threads"] == 128
+    fake_open.content = "250000 100000\n"
+    assert bench.host_cpu_info()["threads"] == 3
+    monkeypatch.setenv("BB_ORACLE_THREADS", "5")
+    assert bench.host_cpu_info()["threads"] == 5
