@@ -197,6 +197,11 @@ class Bases:
         _check(load_library().bb_bases_precompute(self.worker._h, self._h))
         return self
 
+    def drop_table(self):
+        """bb_bases_drop_table: frees the window multiples again (no MSM over these bases may be in flight)"""
+        _check(load_library().bb_bases_drop_table(self._h))
+        return self
+
     def free(self):
         if getattr(self, "_h", None):
             load_library().bb_bases_free(self._h)
@@ -445,6 +450,30 @@ class Parameters:
         worker._children.add(self)
         return self
 
+    def precompute(self):
+        """bb_crs_precompute: window multiples of all five vectors resident (msm_precompute forms)"""
+        _check(load_library().bb_crs_precompute(self.worker._h, self._h))
+        return self
+
+    def drop_tables(self):
+        _check(load_library().bb_crs_drop_tables(self._h))
+        return self
+
+    def apply_tuning(self, index):
+        """bb_crs_apply_tuning: select MSM form `index` (see tuning_names()) for this key and its worker"""
+        _check(load_library().bb_crs_apply_tuning(self.worker._h, self._h, C.c_int(index)))
+
+    def autotune(self, assignment, reps=3, device_ptrs=None):
+        """bb_groth16_autotune: prove `assignment` with every MSM form, keep the fastest whose partial sums equal the
+        default form's.  Returns {"chosen": index, "name": ..., "ms": [per form; negative = not eligible]}."""
+        lib = load_library()
+        n = lib.bb_tuning_count()
+        ms = (C.c_double * n)()
+        chosen = C.c_int(0)
+        w = assignment._struct(device_ptrs)
+        _check(lib.bb_groth16_autotune(self.worker._h, self._h, C.byref(w), C.c_int(reps), C.byref(chosen), ms))
+        return {"chosen": chosen.value, "name": tuning_names()[chosen.value], "ms": [round(float(x), 3) for x in ms]}
+
     def free(self):
         if getattr(self, "_h", None):
             load_library().bb_crs_destroy(self._h)
@@ -455,6 +484,13 @@ class Parameters:
             self.free()
         except Exception:
             pass
+
+
+def tuning_names():
+    """the MSM forms bb_groth16_autotune chooses from (index 0 = default)"""
+    lib = load_library()
+    lib.bb_tuning_name.restype = C.c_char_p
+    return [lib.bb_tuning_name(C.c_int(i)).decode() for i in range(lib.bb_tuning_count())]
 
 
 class ProvingAssignment:

@@ -46,6 +46,7 @@ struct DigitArgs {
     uint32_t c, W;
     uint32_t win_index, win_count;  // this device owns windows w with w % win_count == win_index
     uint32_t table_stride;          // precomputed window multiples: entry of window slot s is base index + s * stride; 0 = none
+    uint32_t key_stride;            // buckets of window slot s start at s * key_stride: D, or 0 when all windows share ONE bucket set
     uint32_t* counts;               // mode 0: histogram; mode 1: cursors
     uint32_t* sorted;               // mode 1
     uint32_t* ones_list;            // base indices with scalar == 1
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(DigitArgs A) {
         else { mag = raw; neg = 0; carry = 0; }
         if (mag == 0 || w % A.win_count != A.win_index) continue;   // the carry chain runs over all windows
         const uint32_t slot = w / A.win_count;
-        uint32_t key = slot * D + (mag - 1);
+        uint32_t key = slot * A.key_stride + (mag - 1);
         if (A.mode == 0) atomicAdd(&A.counts[key], 1u);
         else A.sorted[atomicAdd(&A.counts[key], 1u)] = (local + slot * A.table_stride) | (neg << 31);
     }
@@ -447,9 +448,14 @@ __global__ void __launch_bounds__(32) k_msm_reduce_combine(const XYZZ<F>* level_
 // ---- precomputed window multiples ---------------------------------------------------------------
 // The CRS is fixed and 180 GB of HBM is mostly empty, so every base vector can keep
 // T[s][i] = 2^(c w_s) P_i for each window it owns.  A digit of window w then selects T[w][i] and all
-// windows accumulate into buckets of the SAME weights: after the per-window accumulation the
-// bucket arrays are added slot-wise (k_msm_fold_slots) and the summation by parts and the Horner
-// fold run once instead of W times.
+// windows accumulate into buckets of the SAME weights, so the summation by parts and the Horner fold run
+// once instead of W times.  Two forms:
+//   msm_precompute = 1  one bucket array per window slot, added slot-wise afterwards (k_msm_fold_slots);
+//   msm_precompute = 2  ONE bucket array: the digits of every window are sorted into the same D buckets
+//                       (key = |digit| - 1).  A bucket then holds W times as many entries, which is what the
+//                       batched-affine halving rounds want: R follows the fill (6 rounds at 2^20 scalars and
+//                       c = 16), the XYZZ stage is left with a handful of rows per bucket and the bucket
+//                       reduction with D instead of W D buckets.
 template <class F>
 __global__ void __launch_bounds__(128) k_table_multiples(const Affine<F>* __restrict__ pts, size_t n, uint32_t c, uint32_t W,
                                                          uint32_t wi, uint32_t wc, XYZZ<F>* scratch) {
@@ -541,6 +547,7 @@ struct bb_msm_job {
     uint32_t W_local = 0;            // windows this device owns (all of them unless window-sharded)
     uint32_t W_out = 0;              // window sums copied back: W_local, or 1 with precomputed window multiples
     bool precomp = false;
+    bool unified = false;            // precomp and every window's digits go to ONE set of D buckets (msm_precompute = 2)
     uint32_t affine_rounds = 0;      // batched-affine halving rounds before the XYZZ stage
     size_t n = 0;
     size_t n_dense = 0;              // scalars the density map selects (= n for FullDensity): what can reach the buckets
@@ -884,8 +891,18 @@ int batch_invert_device(bb_ctx* ctx, cudaStream_t st, F* vals, size_t n, F* scra
 // (~0.5 ms of latency), so small jobs and thinly filled buckets keep the plain XYZZ path.
 // Padding a bucket to 2^R entries costs (2^R - 1) / 2 null entries on average, so R follows the mean fill
 // (measured on the 2^20 prove: R = 2 beats R = 3 at 16 entries per bucket, R = 3 wins from 32).
-uint32_t choose_affine_rounds(const bb_ctx* ctx, size_t pairs, uint64_t entries, size_t NB) {
+uint32_t choose_affine_rounds(const bb_ctx* ctx, size_t pairs, uint64_t entries, size_t NB, bool unified) {
     if (ctx->opt_msm_affine_rounds >= 0) return (uint32_t)(ctx->opt_msm_affine_rounds > 8 ? 8 : ctx->opt_msm_affine_rounds);
+    if (unified) {
+        // one bucket set for all windows: there is one thread per bucket in the XYZZ stage and only D of them, so
+        // the rounds go on until about eight rows per bucket are left (floor(log2 fill) - msm_unified_rows_log, at most 8)
+        if (pairs < (1u << 13)) return 0;
+        const uint64_t fill = entries / (NB ? NB : 1);
+        uint32_t lg = 0;
+        while ((fill >> (lg + 1)) != 0) lg++;
+        const uint32_t keep = ctx->opt_msm_unified_rows_log < 0 ? 0u : (uint32_t)ctx->opt_msm_unified_rows_log;
+        return lg <= keep ? 0u : (lg - keep > 8 ? 8u : lg - keep);
+    }
     // every round puts an inversion chain (~0.3 ms of dependent latency) on the job's critical path: a job
     // whose whole accumulation is shorter than that (a small shard of a multi-GPU prove) keeps the XYZZ kernel
     if (pairs < (1u << 15) || entries < (3u << 20)) return 0;
@@ -902,10 +919,11 @@ int launch_msm(bb_msm_job* job) {
     bb_ctx* ctx = job->ctx;
     cudaStream_t st = job->st;
     const uint32_t W = job->W_local, D = job->D;   // everything below works on the owned windows only
-    const size_t NB = (size_t)W * D;
+    const uint32_t Wb = job->unified ? 1u : W;      // bucket sets: one per window, or one for all of them
+    const size_t NB = (size_t)Wb * D;
     const size_t n = job->n;
     const uint64_t entries = (uint64_t)n * W;       // upper bound of the bucket entries (one per non-zero digit)
-    const uint32_t R = job->precomp ? 0u : choose_affine_rounds(ctx, job->n_dense, (uint64_t)job->n_dense * W, NB);
+    const uint32_t R = job->precomp && !job->unified ? 0u : choose_affine_rounds(ctx, job->n_dense, (uint64_t)job->n_dense * W, NB, job->unified);
     const uint32_t pad_mask = (1u << R) - 1u;
     const uint64_t slots = entries + (uint64_t)NB * pad_mask;   // sorted-array capacity with every bucket padded to 2^R
     if (slots >= (1ull << 32)) { set_error("bb_msm: %zu scalars x %u windows exceed 2^32 bucket entries; split the job", n, W); return BB_ERR_ARG; }
@@ -920,7 +938,7 @@ int launch_msm(bb_msm_job* job) {
     BB_TRY(job->d_buckets.alloc(ctx, NB * sizeof(XYZZ<F>)));
     BB_TRY(job->d_order.alloc(ctx, (NB + SIZE_BINS) * 4));
     const uint32_t ONES_BLOCKS = 64;
-    BB_TRY(job->d_final.alloc(ctx, (size_t)(W + 1) * sizeof(XYZZ<F>) + 16));
+    BB_TRY(job->d_final.alloc(ctx, (size_t)(Wb + 1) * sizeof(XYZZ<F>) + 16));
 
     BB_CUDA(cudaMemsetAsync(job->d_counts.p, 0, (NB + 1) * 4, st));
     BB_CUDA(cudaMemsetAsync(job->d_err.p, 0xff, 4, st));
@@ -1054,8 +1072,8 @@ int launch_msm(bb_msm_job* job) {
     if (prof) BB_CUDA(cudaEventRecord(job->ev[2], st));
     BB_STAGE("accumulate");
     XYZZ<F>* fin = job->d_final.as<XYZZ<F>>();
-    uint32_t Wr = W;                                   // window sums the reduction produces
-    if (job->precomp) {
+    uint32_t Wr = Wb;                                  // window sums the reduction produces
+    if (job->precomp && !job->unified) {
         if (W > 1) { k_msm_fold_slots<F><<<cdiv(D, 128), 128, 0, st>>>(buckets, W, D); ctx->count_launch(); }
         Wr = 1;
         BB_STAGE("fold slots");
@@ -1158,9 +1176,10 @@ int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint
     // the pairs this device accumulates: all scalars on one GPU, about one shard's worth when sharded
     if (ctx->opt_msm_precompute && bases->n && !bases->d_table) {
         int ts = bases_build_table(ctx, const_cast<bb_bases*>(bases));     // first use; bb_bases_precompute does it up front
-        if (ts != BB_OK) { job->status = ts; return BB_OK; }
+        if (ts != BB_OK && ts != BB_ERR_OOM) { job->status = ts; return BB_OK; }   // no room for the table: the per-window path needs none
     }
     job->precomp = bases->d_table != nullptr;
+    job->unified = job->precomp && ctx->opt_msm_precompute >= 2;
     job->c = job->precomp ? bases->tab_c : choose_window(ctx, n < bases->n + 1 ? n : bases->n + 1);
     job->W = 255 / job->c + 1;
     job->D = 1u << (job->c - 1);
@@ -1172,6 +1191,7 @@ int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint
     A.c = job->c; A.W = job->W;
     A.win_index = bases->win_index; A.win_count = bases->win_count ? bases->win_count : 1;
     A.table_stride = job->precomp ? (uint32_t)bases->n : 0u;
+    A.key_stride = job->unified ? 0u : job->D;
     if (A.win_index >= A.win_count) { set_error("bb_msm: window shard %u of %u", A.win_index, A.win_count); return fail(BB_ERR_ARG); }
     job->W_local = 0;
     for (uint32_t w = 0; w < job->W; w++) job->W_local += (w % A.win_count == A.win_index);
@@ -1336,6 +1356,13 @@ int bb_msm_async_device(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, 
 int bb_bases_precompute(bb_ctx* ctx, bb_bases* bases) {
     if (!ctx || !bases || bases->ctx != ctx) { set_error("bb_bases_precompute: bad argument"); return BB_ERR_ARG; }
     return bases_build_table(ctx, bases);
+}
+int bb_bases_drop_table(bb_bases* bases) {
+    if (!bases) { set_error("bb_bases_drop_table: null argument"); return BB_ERR_ARG; }
+    std::lock_guard<std::mutex> g(bases->tab_mu);
+    if (bases->d_table) bases->ctx->release(bases->d_table);
+    bases->d_table = nullptr; bases->tab_c = bases->tab_W = bases->tab_slots = 0;
+    return BB_OK;
 }
 int bb_msm_wait(bb_msm_job* job, void* out_affine) {
     if (!job || !out_affine) { set_error("bb_msm_wait: null argument"); return BB_ERR_ARG; }

@@ -537,6 +537,87 @@ int bb_groth16_finalize_with(const bb_crs* crs, const uint8_t* partials, size_t 
     return finalize_impl(crs, partials, count, r, s, stat, proof);
 }
 
+// ---- tuning: measure, don't guess ---------------------------------------------------------------------
+// The MSM has forms whose ranking depends on the machine, the key size and the number of shards (resident
+// window multiples trade 16x the base storage and colder gathers for fewer buckets and deeper halving rounds).
+// A key lives for many proofs, so the choice is made once per key by timing real proofs of each form on this
+// device (the way FFT and convolution libraries plan), and a form is only eligible if its partial sums are
+// byte-identical to the default form's.
+namespace {
+struct Tuning { const char* name; long precompute; long rows_log; };
+const Tuning kTunings[] = {
+    {"per-window bucket sets, no tables", 0, 3},
+    {"one bucket set over resident window multiples, halving rounds down to ~8 rows per bucket", 2, 3},
+    {"one bucket set over resident window multiples, halving rounds down to ~16 rows per bucket", 2, 4},
+    {"one bucket set over resident window multiples, halving rounds down to ~4 rows per bucket", 2, 2},
+};
+constexpr int kNumTunings = (int)(sizeof kTunings / sizeof kTunings[0]);
+}  // namespace
+
+int bb_tuning_count(void) { return kNumTunings; }
+const char* bb_tuning_name(int index) { return index >= 0 && index < kNumTunings ? kTunings[index].name : nullptr; }
+
+int bb_crs_precompute(bb_ctx* ctx, bb_crs* crs) {
+    if (!ctx || !crs || crs->ctx != ctx) { set_error("bb_crs_precompute: bad argument"); return BB_ERR_ARG; }
+    for (bb_bases* b : {crs->h, crs->l, crs->a, crs->b_g1, crs->b_g2})
+        if (b) BB_TRY(bases_build_table(ctx, b));
+    return BB_OK;
+}
+int bb_crs_drop_tables(bb_crs* crs) {
+    if (!crs) { set_error("bb_crs_drop_tables: null argument"); return BB_ERR_ARG; }
+    for (bb_bases* b : {crs->h, crs->l, crs->a, crs->b_g1, crs->b_g2})
+        if (b) bb_bases_drop_table(b);
+    return BB_OK;
+}
+
+int bb_crs_apply_tuning(bb_ctx* ctx, bb_crs* crs, int index) {
+    if (!ctx || !crs || crs->ctx != ctx || index < 0 || index >= kNumTunings) { set_error("bb_crs_apply_tuning: bad argument"); return BB_ERR_ARG; }
+    BB_CUDA(cudaSetDevice(ctx->device));
+    BB_CUDA(cudaDeviceSynchronize());                  // nothing may still read a table that is about to go
+    const Tuning& t = kTunings[index];
+    int s = BB_OK;
+    if (t.precompute) s = bb_crs_precompute(ctx, crs);
+    if (s != BB_OK || !t.precompute) bb_crs_drop_tables(crs);
+    ctx->opt_msm_precompute = s == BB_OK ? t.precompute : 0;
+    ctx->opt_msm_unified_rows_log = s == BB_OK ? t.rows_log : 3;
+    return s;
+}
+
+int bb_groth16_autotune(bb_ctx* ctx, bb_crs* crs, const bb_witness* w, int reps, int* chosen, double* ms_out) {
+    if (!ctx || !crs || crs->ctx != ctx || !w) { set_error("bb_groth16_autotune: bad argument"); return BB_ERR_ARG; }
+    if (reps < 1) reps = 3;
+    uint8_t ref[BB_PARTIALS_BYTES], got[BB_PARTIALS_BYTES];
+    double ms[kNumTunings];
+    int best = 0;
+    for (int i = 0; i < kNumTunings; i++) {
+        ms[i] = -1.0;                                   // -1: not available here (the tables do not fit)
+        int s = bb_crs_apply_tuning(ctx, crs, i);
+        if (s != BB_OK) { if (i == 0) return s; continue; }
+        std::memset(got, 0, sizeof got);
+        s = prove_partials_impl(ctx, crs, w, got, nullptr);             // first proof of this form: builds caches, checked
+        if (s != BB_OK) {
+            if (i == 0) return s;                       // the witness / key itself fails: nothing to tune
+            ms[i] = -2.0;                               // -2: this form failed where the default did not
+            continue;
+        }
+        if (i == 0) std::memcpy(ref, got, sizeof ref);
+        else if (std::memcmp(ref, got, sizeof ref) != 0) { ms[i] = -3.0; continue; }     // -3: different partial sums -- never eligible
+        double fastest = 1e300;
+        for (int k = 0; k < reps && s == BB_OK; k++) {
+            const auto t0 = std::chrono::steady_clock::now();
+            s = prove_partials_impl(ctx, crs, w, got, nullptr);
+            const double dt = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (dt < fastest) fastest = dt;
+        }
+        if (s != BB_OK) { if (i == 0) return s; ms[i] = -2.0; continue; }
+        ms[i] = fastest;
+        if (ms[i] < ms[best]) best = i;
+    }
+    if (ms_out) for (int i = 0; i < kNumTunings; i++) ms_out[i] = ms[i];
+    if (chosen) *chosen = best;
+    return bb_crs_apply_tuning(ctx, crs, best);
+}
+
 int bb_groth16_prove(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, const uint8_t* r_bytes, const uint8_t* s_bytes, uint8_t* proof) {
     if (!crs || !r_bytes || !s_bytes || !proof) { set_error("bb_groth16_prove: null argument"); return BB_ERR_ARG; }
     if (crs->shard_count != 1) { set_error("bb_groth16_prove needs an unsharded CRS; use prove_partials + finalize"); return BB_ERR_ARG; }

@@ -42,6 +42,73 @@ def max_over_ranks(seconds, group=None):
     return float(t.item())
 
 
+def _all_reduce(value, op, group=None):
+    import torch
+    import torch.distributed as dist
+
+    backend = dist.get_backend(group)
+    device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=getattr(dist.ReduceOp, op), group=group)
+    return float(t.item())
+
+
+def autotune_sharded(assignment, params, r, s, device_ptrs=None, reps=3, group=None, split_h=True):
+    """bb_groth16_autotune for a sharded key: every MSM form (bellman_b200.tuning_names()) proves `assignment` through
+    create_proof_sharded on all ranks; a form is eligible only if every rank could set it up and rank 0's proof bytes
+    equal the default form's; the time of a form is the fastest of `reps` proofs, each the MAX over ranks between two
+    barriers; all ranks end up configured for the same, fastest form.  Collective: call it on every rank.
+    Returns {"chosen", "name", "ms"} (ms < 0: -1 not available on some rank, -2 failed, -3 different proof)."""
+    import time
+
+    import torch.distributed as dist
+
+    from . import BackendError, SynthesisError, tuning_names
+
+    names = tuning_names()
+    rank = dist.get_rank(group)
+    ms, ref = [], None
+    for index in range(len(names)):
+        ok = 1.0
+        try:
+            params.apply_tuning(index)
+        except BackendError:
+            if index == 0:
+                raise
+            ok = 0.0
+        if _all_reduce(ok, "MIN", group) < 1.0:
+            ms.append(-1.0)
+            continue
+        try:
+            proof = create_proof_sharded(assignment, params, params, r, s, device_ptrs, group, split_h)      # raises on every rank or on none
+            same = 1.0
+            if rank == 0:
+                if index == 0:
+                    ref = proof
+                same = 1.0 if proof == ref else 0.0
+            if _all_reduce(same, "MIN", group) < 1.0:
+                ms.append(-3.0)
+                continue
+            best = None
+            for _ in range(reps):
+                params.worker.synchronize()
+                dist.barrier(group)
+                t0 = time.perf_counter()
+                create_proof_sharded(assignment, params, params, r, s, device_ptrs, group, split_h)
+                params.worker.synchronize()
+                dt = _all_reduce(time.perf_counter() - t0, "MAX", group)
+                best = dt if best is None or dt < best else best
+            ms.append(round(1e3 * best, 3))
+        except (BackendError, SynthesisError, AssertionError):
+            if index == 0:
+                raise
+            ms.append(-2.0)
+    chosen = min((i for i in range(len(names)) if ms[i] > 0), key=lambda i: ms[i])
+    params.apply_tuning(chosen)
+    HOST_MS.clear()
+    return {"chosen": chosen, "name": names[chosen], "ms": ms}
+
+
 _EVAL_BUFFERS = {}       # (device, m) -> three tensors of m Fr: the coset evaluations of a, b, c on this rank
 HOST_MS = {}             # accumulated host milliseconds of create_proof_sharded's phases on this rank (bench.py reads and resets it)
 

@@ -43,7 +43,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-budget-s", type=float, default=1200.0, help="--impl reference: wall-clock bound of the proving loop")
     ap.add_argument("--window-bits", type=int, default=0)
-    ap.add_argument("--precompute", type=int, default=0, help="1 = resident window multiples of every base vector (msm_precompute)")
+    ap.add_argument("--precompute", type=int, default=None, help="force msm_precompute (0 = per-window bucket sets, 1 = window multiples + one bucket array "
+                                                                   "per window, 2 = window multiples + ONE bucket array) instead of measuring")
+    ap.add_argument("--autotune", type=int, default=1, help="1 = before the warm-up, time every MSM form on this key (bb_groth16_autotune; sharded: the whole "
+                                                            "sharded proof, max over ranks) and run the fastest whose results are byte-identical; 0 = default form")
     ap.add_argument("--acc-variant", type=int, default=0)
     ap.add_argument("--ntt-radix8", type=int, default=0, help="1 = register radix-8 windows (k_ntt_pass8) instead of radix-2 sweeps in shared memory (k_ntt_pass)")
     ap.add_argument("--reduce-2d", type=int, default=1, help="0 = serial running-sum recursion over whole windows instead of row/column sums first")
@@ -297,7 +300,7 @@ def run_prove(args):
     if args.reduce_k1:
         worker.set_option("msm_reduce_k1", args.reduce_k1)
     if args.precompute:
-        worker.set_option("msm_precompute", 1)
+        worker.set_option("msm_precompute", args.precompute)
     if args.acc_variant:
         worker.set_option("msm_acc_variant", args.acc_variant)
     worker.set_option("msm_affine_rounds", args.affine_rounds)
@@ -326,6 +329,22 @@ def run_prove(args):
         keep.append(t)
         dev[name] = t.data_ptr()
     torch.cuda.synchronize()
+
+    # Which MSM form this key runs is measured, not assumed: before any warm-up every form proves this witness on this
+    # device (N > 1: the sharded proof, max over ranks), only forms whose results are byte-identical to the default's are
+    # eligible, the fastest stays configured.  Outside every timed region; the timed steps run the chosen form only.
+    tuning = None
+    if args.autotune and args.precompute is None and args.affine_rounds < 0:
+        log("measuring the MSM forms on this key (autotune)")
+        if world == 1:
+            tuning = params.autotune(asg, reps=3, device_ptrs=dev)
+        else:
+            from bellman_b200.distributed import autotune_sharded
+            tuning = autotune_sharded(asg, params, r, s, device_ptrs=dev, reps=3)
+        tuning["forms"] = bb.tuning_names()
+        tuning["note"] = ("ms per proof and form, fastest of 3 after one checked proof (negative: -1 tables do not fit, -2 failed, "
+                          "-3 results differ: never eligible); measured before the warm-up, outside the timed regions")
+        log(f"autotune: {tuning['ms']} ms -> form {tuning['chosen']}: {tuning['name']}")
 
     def step(device_ptrs):
         if world == 1:
@@ -390,6 +409,7 @@ def run_prove(args):
             # same synthetic CRS (outside every timed region) and compares the bytes
             log("checking the sharded proof against a single-GPU prove of the same CRS and witness")
             full = bb.Parameters.synthetic(worker, 21, shape, shard_index=0, shard_count=1)
+            full.apply_tuning(0)                        # the reference proof of this check comes from the default form
             proof_single = bb.create_proof(asg, full, r, s, dev)
             full.free()
             assert proof_single == proof_val, "sharded proof differs from the single-GPU proof"
@@ -418,6 +438,7 @@ def run_prove(args):
                 "ms_per_step": 1e3 * dt_e2e / args.steps},
         "gpu_launches": int(launches),
         "proof_sha256": hashlib.sha256(proof_val).hexdigest() if rank == 0 else None,
+        "autotune": tuning,
         "sharded_host_ms_per_step": host_ms,
         "proof_check": (None if rank else ("sharded proof == single-GPU proof of the same CRS/witness/r/s (192 bytes equal, rank 0)"
                                            if world > 1 else "value leg == e2e leg (192 bytes equal); parity with the oracle: tests/")),
@@ -496,7 +517,7 @@ def run_msm(args):
     if args.reduce_k:
         worker.set_option("msm_reduce_k", args.reduce_k)
     if args.precompute:
-        worker.set_option("msm_precompute", 1)
+        worker.set_option("msm_precompute", args.precompute)
     worker.set_option("msm_affine_rounds", args.affine_rounds)
     worker.set_option("msm_reduce_2d", args.reduce_2d)
     worker.set_option("msm_affine_tma", args.affine_tma)
@@ -507,6 +528,40 @@ def run_msm(args):
     d_sc = worker.device_alloc(n * 32)
     bb.synth_scalars_device(worker, 32, n, d_sc)
     log("inputs resident")
+    tuning = None
+    if args.autotune and args.precompute is None and args.affine_rounds < 0:
+        # the bases of this microbench are fixed like a key's: measure the per-window form against ONE bucket set over
+        # resident window multiples (same point required), keep the faster; outside the timed region
+        tuning = {"forms": ["per-window bucket sets, no tables", "one bucket set over resident window multiples"], "ms": []}
+        ref = None
+        for form in (0, 2):
+            try:
+                worker.set_option("msm_precompute", form)
+                if form:
+                    bases.precompute()
+                got = bb.multiexp_device(worker, (bases, 0), d_sc, n, bb.FORM_CANONICAL).wait()
+                ref = got if ref is None else ref
+                if not np.array_equal(np.asarray(got), np.asarray(ref)):
+                    tuning["ms"].append(-3.0)
+                    continue
+                best = None
+                for _ in range(2):
+                    worker.synchronize()
+                    t0 = time.perf_counter()
+                    bb.multiexp_device(worker, (bases, 0), d_sc, n, bb.FORM_CANONICAL).wait()
+                    dt = time.perf_counter() - t0
+                    best = dt if best is None or dt < best else best
+                tuning["ms"].append(round(1e3 * best, 3))
+            except bb.BackendError:
+                if form == 0:
+                    raise
+                tuning["ms"].append(-1.0)
+        chosen = min((i for i in range(2) if tuning["ms"][i] > 0), key=lambda i: tuning["ms"][i])
+        tuning["chosen"] = chosen
+        if chosen == 0:
+            bases.drop_table()
+        worker.set_option("msm_precompute", (0, 2)[chosen])
+        log(f"autotune: {tuning['ms']} ms -> {tuning['forms'][chosen]}")
     worker.set_option("profile", 1)
     out = None
     sampler = ClockSampler(0)
@@ -531,6 +586,7 @@ def run_msm(args):
             "dtype": "u32 limbs", "data": "synthetic",
             "config": {"workload": f"g1-msm-2^{log_n}", "bases": "[k_i]G distinct, generated in HBM", "scalars": "pseudorandom < 2^254, canonical, resident in HBM",
                        "window_bits": args.window_bits or "auto"},
+            "autotune": tuning,
             "gpu_launches": int(worker.kernel_launches - l0), "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "whole MSM (all kernels of one job)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": (achieved / hbm_peak) if achieved else None, "traffic": None, "peak_source": peak_src,

@@ -76,7 +76,9 @@ void bb_ctx_destroy(bb_ctx* ctx);
  *   msm_reduce_2d      0 = bucket reduction by the serial recursion over whole windows (default 1: row/column sums first)
  *   msm_reduce_k, msm_reduce_k1   entries per thread of the serial recursion (powers of two, default 4)
  *   msm_big_cap        bucket size above which a bucket is cut into tasks (0 = by mean fill)
- *   msm_precompute     1 = keep window multiples of every base vector resident (see bb_bases_precompute)
+ *   msm_precompute     keep window multiples of every base vector resident (see bb_bases_precompute): 1 = one bucket
+ *                      array per window, added slot-wise; 2 = ONE bucket array for all windows and halving rounds by its fill
+ *   msm_unified_rows_log   msm_precompute = 2: the rounds stop at about 2^this rows per bucket (default 3)
  *   shard_windows      multi-GPU: window groups per base range (default 4; 1 = base ranges only)
  *   ntt_radix8         1 = register radix-8 NTT windows (default 0: measured slower), ntt_tile_log, ntt_col_bits
  *   profile            1 = CUDA-event timing of the MSM stages (bb_profile_read) */
@@ -128,6 +130,8 @@ void bb_bases_free(bb_bases* b);
  * base storage.  Results are unchanged.  With bb_ctx_set_option(ctx, "msm_precompute", 1) the table
  * is built on first use instead. */
 int bb_bases_precompute(bb_ctx* ctx, bb_bases* bases);
+/* Frees that table again.  No MSM over these bases may be in flight. */
+int bb_bases_drop_table(bb_bases* bases);
 
 /* ---- MSM: multiexp() (src/multiexp.rs:305-332) ---------------------------------------- */
 /* Sum over i with density bit set of scalars[i] * bases[base_offset + rank(i)], where rank(i)
@@ -189,6 +193,9 @@ typedef struct bb_crs_desc {
 
 int bb_crs_create(bb_ctx* ctx, const bb_crs_desc* desc, bb_crs** out);
 void bb_crs_destroy(bb_crs* crs);
+/* bb_bases_precompute / bb_bases_drop_table over the five vectors of a resident key */
+int bb_crs_precompute(bb_ctx* ctx, bb_crs* crs);
+int bb_crs_drop_tables(bb_crs* crs);
 
 /* What ProvingAssignment holds when synthesis is done (prover.rs:57-71,193-215), i.e.
  * including the trailing "input * 0 = 0" constraints. */
@@ -252,6 +259,21 @@ int bb_groth16_finalize_with(const bb_crs* crs, const uint8_t* partials, size_t 
  * b_g1_inputs, b_g1_aux, b_g2_inputs, b_g2_aux, h, l (:339-354). */
 int bb_groth16_prove(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w,
                      const uint8_t r[32], const uint8_t s[32], uint8_t proof[192]);
+
+/* ---- tuning per key ------------------------------------------------------------------------
+ * The MSM has several forms with identical results (per-window bucket sets; one bucket set over resident window
+ * multiples with deeper halving rounds, which costs (windows x) the base storage).  Which is fastest depends on
+ * the device, the key size and the shard count, and a key serves many proofs, so the choice is MEASURED once per
+ * key: bb_groth16_autotune proves the given witness with every form (one checked proof, then `reps` timed ones,
+ * fastest taken), admits a form only if its 960 bytes of partial sums equal the default form's, leaves the context
+ * and the key configured for the fastest one and frees the tables if they lost.  ms_out (bb_tuning_count()
+ * doubles, may be NULL): milliseconds per form; -1 = not available (no room for the tables), -2 = failed,
+ * -3 = different partial sums.  *chosen = index of the form now active.  bb_crs_apply_tuning selects a form by
+ * hand (multi-GPU callers time the sharded proof themselves and agree on one index).  Form 0 is the default. */
+int bb_tuning_count(void);
+const char* bb_tuning_name(int index);
+int bb_crs_apply_tuning(bb_ctx* ctx, bb_crs* crs, int index);
+int bb_groth16_autotune(bb_ctx* ctx, bb_crs* crs, const bb_witness* w, int reps, int* chosen, double* ms_out);
 
 /* ---- profiling: CUDA-event timing of the dominant kernels, on the stream they run on ------ */
 /* bb_ctx_set_option(ctx, "profile", 1) makes every MSM job bracket its bucket-accumulation

@@ -83,6 +83,7 @@ extern "C" {
                            global_len: usize, out: *mut *mut bb_bases) -> c_int;
     pub fn bb_bases_free(b: *mut bb_bases);
     pub fn bb_bases_precompute(ctx: *mut bb_ctx, bases: *mut bb_bases) -> c_int;
+    pub fn bb_bases_drop_table(bases: *mut bb_bases) -> c_int;
 
     pub fn bb_msm_async(ctx: *mut bb_ctx, bases: *const bb_bases, base_offset: usize, density_bits: *const u64,
                         density_len: usize, scalars: *const c_void, n_scalars: usize, form: c_int,
@@ -104,6 +105,8 @@ extern "C" {
 
     pub fn bb_crs_create(ctx: *mut bb_ctx, desc: *const bb_crs_desc, out: *mut *mut bb_crs) -> c_int;
     pub fn bb_crs_destroy(crs: *mut bb_crs);
+    pub fn bb_crs_precompute(ctx: *mut bb_ctx, crs: *mut bb_crs) -> c_int;
+    pub fn bb_crs_drop_tables(crs: *mut bb_crs) -> c_int;
 
     pub fn bb_groth16_prove_partials(ctx: *mut bb_ctx, crs: *const bb_crs, w: *const bb_witness, partials: *mut u8) -> c_int;
     pub fn bb_groth16_prove_begin(ctx: *mut bb_ctx, crs: *const bb_crs, w: *const bb_witness, out: *mut *mut bb_prove) -> c_int;
@@ -119,6 +122,12 @@ extern "C" {
                                     static_in: *const u8, proof: *mut u8) -> c_int;
     pub fn bb_groth16_prove(ctx: *mut bb_ctx, crs: *const bb_crs, w: *const bb_witness, r: *const u8, s: *const u8,
                             proof: *mut u8) -> c_int;
+
+    pub fn bb_tuning_count() -> c_int;
+    pub fn bb_tuning_name(index: c_int) -> *const c_char;
+    pub fn bb_crs_apply_tuning(ctx: *mut bb_ctx, crs: *mut bb_crs, index: c_int) -> c_int;
+    pub fn bb_groth16_autotune(ctx: *mut bb_ctx, crs: *mut bb_crs, w: *const bb_witness, reps: c_int, chosen: *mut c_int,
+                               ms_out: *mut f64) -> c_int;
 
     pub fn bb_profile_read(ctx: *mut bb_ctx, what: *const c_char, ms: *mut f64, launches: *mut u64, units: *mut u64) -> c_int;
     pub fn bb_profile_reset(ctx: *mut bb_ctx) -> c_int;

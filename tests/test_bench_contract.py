@@ -55,7 +55,7 @@ bb.LIB_PATH, bb._lib = EMU_LIB, None          # the product sources on host fibe
 spec = importlib.util.spec_from_file_location("bench", ROOT + "/bench.py")
 bench = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(bench)
-sys.argv = ["bench.py", "--log-size", "8", "--steps", "2", "--warmup", "1", "--cpu-sample-log", "8"]
+sys.argv = ["bench.py", "--log-size", "8", "--steps", "2", "--warmup", "1", "--cpu-sample-log", "8"] + EXTRA
 bench.main()
 '''
 
@@ -65,7 +65,7 @@ def test_own_arm_dry_run_on_the_emulated_device(tmp_path, emu_lib):
     to end with the CUDA library replaced by the host-fiber build of the same sources and torch.cuda
     stubbed: checks the script and the JSON contract, not the numbers."""
     script = tmp_path / "dry.py"
-    script.write_text(f"ROOT = {ROOT!r}\nEMU_LIB = {emu_lib!r}\n" + DRY_RUN)
+    script.write_text(f"ROOT = {ROOT!r}\nEMU_LIB = {emu_lib!r}\nEXTRA = []\n" + DRY_RUN)
     res = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert res.returncode == 0, res.stderr[-3000:]
     lines = [l for l in res.stdout.splitlines() if l.strip()]
@@ -81,6 +81,20 @@ def test_own_arm_dry_run_on_the_emulated_device(tmp_path, emu_lib):
     assert len(d["timeline"]["device_ms_since_prove_start"]) == 8
     assert d["roofline"]["pairs_per_step"] > 0 and d["roofline"]["bucket_entries_per_step"] > d["roofline"]["pairs_per_step"]
     assert "workload" in d["config"] and "model" not in d["config"]
+    at = d["autotune"]                                  # the MSM form was measured before the warm-up; every form eligible here
+    assert len(at["ms"]) == len(at["forms"]) >= 2 and all(t > 0 for t in at["ms"]) and at["ms"][at["chosen"]] == min(at["ms"])
+
+
+def test_msm_microbench_dry_run_on_the_emulated_device(tmp_path, emu_lib):
+    """bench.py --workload msm (BASELINE configs[2] shape, here 2^10 points): both MSM forms are measured, the result
+    is asserted against [sum k_i e_i]G inside the script"""
+    script = tmp_path / "dry_msm.py"
+    script.write_text(f"ROOT = {ROOT!r}\nEMU_LIB = {emu_lib!r}\nEXTRA = ['--workload', 'msm', '--log-size', '10']\n" + DRY_RUN)
+    res = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-3000:]
+    d = json.loads([l for l in res.stdout.splitlines() if l.strip()][0])
+    assert d["metric"] == "g1_msm_mpt_per_sec" and d["config"]["result_check"].endswith("equal")
+    assert len(d["autotune"]["ms"]) == 2 and all(t > 0 for t in d["autotune"]["ms"])
 
 
 def test_reference_arm_sizes_its_pool_to_the_cpu_quota(monkeypatch):

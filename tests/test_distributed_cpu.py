@@ -97,6 +97,20 @@ SHARDED_PROVE = textwrap.dedent('''
             assert proof == mc.prove(r, s) == mc.expected_proof(r, s), split_h
         else:
             assert proof is None
+    # the MSM form is chosen collectively: every form proves, every form is eligible here, all ranks agree
+    from bellman_b200.distributed import autotune_sharded
+    rep = autotune_sharded(asg, mine, r, s, reps=1)
+    names = bb.tuning_names()
+    assert len(rep["ms"]) == len(names) and all(t > 0 for t in rep["ms"]) and rep["ms"][rep["chosen"]] == min(rep["ms"]), rep
+    picks = [None] * world
+    dist.all_gather_object(picks, rep["chosen"])
+    assert len(set(picks)) == 1
+    for index in [rep["chosen"]] + list(range(len(names))):
+        if index != rep["chosen"]:
+            mine.apply_tuning(index)
+        proof = create_proof_sharded(asg, mine, mine, r, s)
+        assert proof is None if rank else proof == mc.expected_proof(r, s), names[index]
+    mine.apply_tuning(0)
     # a shard with an identity base: every rank raises the same SynthesisError
     bad = mc.export_params()
     if rank == 1:

@@ -65,3 +65,55 @@ def test_emulated_accumulate_variants(worker, variant):
     finally:
         worker.set_option("msm_acc_variant", 0)
         worker.set_option("msm_precompute", 0)
+
+
+# ---- msm_precompute = 2: one bucket set for all windows ------------------------------------------------
+@pytest.fixture()
+def unified(worker):
+    worker.set_option("msm_precompute", 2)
+    yield worker
+    worker.set_option("msm_precompute", 0)
+    worker.set_option("msm_unified_rows_log", 3)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 33, 1000])
+def test_emulated_unified_g1(unified, n):
+    G.test_multiexp_g1_matches_oracle(unified, n)
+
+
+@pytest.mark.parametrize("n", [3, 40, 300])
+def test_emulated_unified_g2(unified, n):
+    G.test_multiexp_g2_matches_oracle(unified, n)
+
+
+@pytest.mark.parametrize("rounds", [1, 2, 4, 6])
+def test_emulated_unified_forced_rounds(unified, rounds):
+    unified.set_option("msm_affine_rounds", rounds)
+    try:
+        G.test_multiexp_g1_matches_oracle(unified, 1000)
+        G.test_multiexp_g2_matches_oracle(unified, 40)
+        G.test_multiexp_error_semantics(unified)
+    finally:
+        unified.set_option("msm_affine_rounds", -1)
+
+
+def test_emulated_unified_variants(unified):
+    E.test_emulated_multiexp_windows(unified)
+    E.test_emulated_multiexp_density_fast_paths_and_skew(unified)
+    G.test_multiexp_error_semantics(unified)
+
+
+def test_emulated_unified_deep_rounds(unified):
+    G.unified_deep_rounds_case(unified, 1 << 13)            # the rounds chosen by the fill: 8 of them
+
+
+def test_emulated_unified_prove_and_shards(unified):
+    E.test_emulated_prove_mimc322_and_shards(unified)
+    G.test_prove_error_precedence(unified)
+    G.test_prove_begin_end_with_coset_evaluations(unified)
+    E.test_emulated_bench_paths(unified)
+
+
+def test_emulated_autotune(worker):
+    G.autotune_case(worker, 60)
+    assert bb.load_library().bb_tuning_name(99) is None

@@ -878,6 +878,104 @@ def test_precompute_prove(precompute):
     test_prove_error_precedence(precompute)
 
 
+# msm_precompute = 2: ONE bucket set for all windows over the same tables, halving rounds by its fill
+# --------------------------------------------------------------------------------------------
+@pytest.fixture()
+def unified(worker):
+    worker.set_option("msm_precompute", 2)
+    yield worker
+    worker.set_option("msm_precompute", 0)
+    worker.set_option("msm_unified_rows_log", 3)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 33, 1000, 1 << 14, 1 << 16])
+def test_unified_multiexp_g1(unified, n):
+    test_multiexp_g1_matches_oracle(unified, n)          # 2^14: fill 18 -> 1 round, 2^16: fill 72 -> 3 rounds
+
+
+@pytest.mark.parametrize("n", [3, 40, 2000])
+def test_unified_multiexp_g2(unified, n):
+    test_multiexp_g2_matches_oracle(unified, n)
+
+
+def test_unified_variants(unified):
+    test_multiexp_window_choice_does_not_change_results(unified)
+    test_multiexp_density_offset_and_fast_paths(unified)
+    test_multiexp_skewed_scalars(unified)
+    test_multiexp_error_semantics(unified)
+    test_multiexp_naive_property_full_size(unified)      # 2^18, c = 15: fill 288 -> 5 rounds
+    test_multiexp_g2_2e16_matches_oracle(unified)        # G2, fill 72 -> 3 rounds
+
+
+def unified_deep_rounds_case(worker, n=1 << 13):
+    """a small window (c = 8: 128 buckets, 32 windows) makes the shared buckets deep: fill 2048 -> the maximum of
+    8 halving rounds with the default stop, and every stop from 2^0 to 2^12 rows gives the same point"""
+    bases_arr = o1.g1_fixed_mul(o1.fr_random(5100, n))
+    ex = o1.fr_random(5101, n)
+    ex[3] = 0; ex[5] = o1.fr_from_ints([1])[0]; ex[6] = o1.fr_from_ints([R - 1])[0]
+    rc, want = o1.multiexp(1, bases_arr, 0, None, ex)
+    assert rc == 0
+    try:
+        worker.set_option("msm_window_bits", 8)
+        bases = bb.Bases(worker, bb.G1, bases_arr)
+        for rows_log in (3, 0, 5, 12):
+            worker.set_option("msm_unified_rows_log", rows_log)
+            assert np.array_equal(bb.multiexp(worker, (bases, 0), bb.FullDensity, ex).wait(), want), rows_log
+        bases.free()
+    finally:
+        worker.set_option("msm_window_bits", 0)
+        worker.set_option("msm_unified_rows_log", 3)
+
+
+def test_unified_deep_rounds(unified):
+    unified_deep_rounds_case(unified)
+
+
+def test_unified_synthetic_bases_naive_property(unified):
+    test_multiexp_synthetic_bases_naive_property(unified, 22, 0)     # 2^22, c = 16: fill 2048 -> 8 rounds
+
+
+def test_unified_prove(unified):
+    test_prove_mimc322_matches_oracle(unified)
+    test_prove_synthetic_chain_trapdoor(unified, 8191)
+    test_prove_error_precedence(unified)
+    test_prove_begin_end_with_coset_evaluations(unified)
+
+
+def test_unified_prove_2e20(unified):
+    test_prove_synthetic_chain_trapdoor(unified, 524287)
+
+
+def autotune_case(worker, rounds):
+    """bb_groth16_autotune: every MSM form proves the same witness, only forms with the default form's partial sums
+    are eligible, the key is left configured for the chosen one and proves to the expected bytes"""
+    rng = random.Random(rounds + 1)
+    mc = o1.Mimc(rounds, seed=rounds + 2)
+    mc.set_toxic([rng.randrange(1, R) for _ in range(5)])
+    mc.generate()
+    params = bb.Parameters(worker, mc.export_params())
+    asg = _assignment(mc.witness())
+    try:
+        rep = params.autotune(asg, reps=2)
+        names = bb.tuning_names()
+        assert len(rep["ms"]) == len(names) >= 2 and 0 <= rep["chosen"] < len(names) and rep["name"] == names[rep["chosen"]]
+        assert rep["ms"][0] > 0 and rep["ms"][rep["chosen"]] > 0
+        assert all(t > 0 for t in rep["ms"]), rep                # every form available, working and byte-identical here
+        assert rep["ms"][rep["chosen"]] == min(rep["ms"])
+        r, s = rng.randrange(R), rng.randrange(R)
+        assert bb.create_proof(asg, params, r, s) == mc.expected_proof(r, s)
+        for index in range(len(names)):                           # and by hand: every form, same proof
+            params.apply_tuning(index)
+            assert bb.create_proof(asg, params, r, s) == mc.expected_proof(r, s), names[index]
+    finally:
+        params.apply_tuning(0)
+        params.free()
+
+
+def test_autotune(worker):
+    autotune_case(worker, 8191)
+
+
 def test_prove_begin_end_with_coset_evaluations(worker):
     """The two-step prove of the multi-GPU flow on one device: bb_groth16_prove_begin queues the witness MSMs,
     bb_h_coset_evals takes a, b, c through ifft + coset_fft one by one (as three ranks would), and
