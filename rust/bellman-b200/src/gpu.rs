@@ -200,20 +200,40 @@ pub struct WitnessView<'a> {
     pub b_aux_density: &'a bitvec::vec::BitVec<usize, bitvec::order::Lsb0>,
 }
 
+impl<'a> WitnessView<'a> {
+    fn as_ffi(&self) -> bb_witness {
+        const _: () = assert!(std::mem::size_of::<Scalar>() == 32);
+        bb_witness {
+            a: self.a.as_ptr() as _, b: self.b.as_ptr() as _, c: self.c.as_ptr() as _, n_constraints: self.a.len(),
+            input_assignment: self.input_assignment.as_ptr() as _, n_inputs: self.input_assignment.len(),
+            aux_assignment: self.aux_assignment.as_ptr() as _, n_aux: self.aux_assignment.len(),
+            a_aux_density: self.a_aux_density.as_raw_slice().as_ptr() as _,
+            b_input_density: self.b_input_density.as_raw_slice().as_ptr() as _,
+            b_aux_density: self.b_aux_density.as_raw_slice().as_ptr() as _,
+            on_device: 0,
+        }
+    }
+}
+
+impl GpuParameters {
+    /// Once per key (a key serves many proofs): proves `w` with every MSM form of the back-end on this device and
+    /// leaves the key configured for the fastest form whose partial sums are byte-identical to the default form's
+    /// (`bb_groth16_autotune`).  Returns the index chosen and the milliseconds measured per form.
+    pub fn autotune(&mut self, w: &WitnessView, reps: i32) -> Result<(usize, Vec<f64>), SynthesisError> {
+        let n = unsafe { bb_tuning_count() } as usize;
+        let mut ms = vec![0f64; n];
+        let mut chosen = 0i32;
+        let wit = w.as_ffi();
+        status(unsafe { bb_groth16_autotune(self.ctx, self.handle, &wit, reps, &mut chosen, ms.as_mut_ptr()) })?;
+        Ok((chosen as usize, ms))
+    }
+}
+
 /// Drop-in for the body of `groth16::create_proof` after synthesis (groth16/src/prover.rs:217-360).
 /// `Scalar` is `[u64; 4]` in Montgomery form (R = 2^256), which is BB_FORM_MONTGOMERY byte for byte; the
 /// cast below is version-pinned (`bls12_381 = "=0.8.0"`) because `#[repr(transparent)]` is not promised.
 pub fn create_proof_b200(w: &WitnessView, crs: &GpuParameters, r: Scalar, s: Scalar) -> Result<Proof<Bls12>, SynthesisError> {
-    const _: () = assert!(std::mem::size_of::<Scalar>() == 32);
-    let wit = bb_witness {
-        a: w.a.as_ptr() as _, b: w.b.as_ptr() as _, c: w.c.as_ptr() as _, n_constraints: w.a.len(),
-        input_assignment: w.input_assignment.as_ptr() as _, n_inputs: w.input_assignment.len(),
-        aux_assignment: w.aux_assignment.as_ptr() as _, n_aux: w.aux_assignment.len(),
-        a_aux_density: w.a_aux_density.as_raw_slice().as_ptr() as _,
-        b_input_density: w.b_input_density.as_raw_slice().as_ptr() as _,
-        b_aux_density: w.b_aux_density.as_raw_slice().as_ptr() as _,
-        on_device: 0,
-    };
+    let wit = w.as_ffi();
     let mut bytes = [0u8; 192];
     status(unsafe { bb_groth16_prove(crs.ctx, crs.handle, &wit, r.to_repr().as_ptr(), s.to_repr().as_ptr(), bytes.as_mut_ptr()) })?;
     Proof::read(&bytes[..]).map_err(Into::into)               // the same 192 bytes Proof::write emits (lib.rs:39-45)
