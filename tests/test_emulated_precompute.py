@@ -109,9 +109,7 @@ def test_emulated_unified_deep_rounds(unified):
 
 def test_emulated_unified_prove_and_shards(unified):
     E.test_emulated_prove_mimc322_and_shards(unified)
-    G.test_prove_error_precedence(unified)
     G.test_prove_begin_end_with_coset_evaluations(unified)
-    E.test_emulated_bench_paths(unified)
 
 
 def test_emulated_autotune(worker):
