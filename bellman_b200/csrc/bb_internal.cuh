@@ -84,6 +84,7 @@ struct bb_ctx {
     long opt_msm_affine_batch = 16;   // pairs per thread sharing one link of the inversion chain
     long opt_msm_precompute = 0;     // resident window multiples 2^(c w) P of every base vector (msm.cu: bases_build_table):
                                      // 1 = one bucket array per window slot, 2 = ONE bucket array for all windows
+    long opt_msm_precompute_groups = 3;  // which groups use the tables: bit 0 = G1 vectors, bit 1 = G2 vectors
     long opt_msm_unified_rows_log = 3;   // msm_precompute = 2: halving rounds until about 2^this rows per bucket are left
     struct ProfEntry { double ms = 0; uint64_t launches = 0, units = 0; };
     std::map<std::string, ProfEntry> prof;

@@ -1174,11 +1174,12 @@ int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint
         return BB_OK;
     }
     // the pairs this device accumulates: all scalars on one GPU, about one shard's worth when sharded
-    if (ctx->opt_msm_precompute && bases->n && !bases->d_table) {
+    const bool tables_wanted = ctx->opt_msm_precompute && (ctx->opt_msm_precompute_groups & (bases->group == BB_G1 ? 1 : 2));
+    if (tables_wanted && bases->n && !bases->d_table) {
         int ts = bases_build_table(ctx, const_cast<bb_bases*>(bases));     // first use; bb_bases_precompute does it up front
         if (ts != BB_OK && ts != BB_ERR_OOM) { job->status = ts; return BB_OK; }   // no room for the table: the per-window path needs none
     }
-    job->precomp = bases->d_table != nullptr;
+    job->precomp = bases->d_table != nullptr && (tables_wanted || !ctx->opt_msm_precompute);   // a table built by hand (bb_bases_precompute) is used as it is
     job->unified = job->precomp && ctx->opt_msm_precompute >= 2;
     job->c = job->precomp ? bases->tab_c : choose_window(ctx, n < bases->n + 1 ? n : bases->n + 1);
     job->W = 255 / job->c + 1;

@@ -544,12 +544,14 @@ int bb_groth16_finalize_with(const bb_crs* crs, const uint8_t* partials, size_t 
 // device (the way FFT and convolution libraries plan), and a form is only eligible if its partial sums are
 // byte-identical to the default form's.
 namespace {
-struct Tuning { const char* name; long precompute; long rows_log; };
+struct Tuning { const char* name; long precompute; long rows_log; long groups; };   // groups: 1 = G1 vectors, 2 = G2 vectors
 const Tuning kTunings[] = {
-    {"per-window bucket sets, no tables", 0, 3},
-    {"one bucket set over resident window multiples, halving rounds down to ~8 rows per bucket", 2, 3},
-    {"one bucket set over resident window multiples, halving rounds down to ~16 rows per bucket", 2, 4},
-    {"one bucket set over resident window multiples, halving rounds down to ~4 rows per bucket", 2, 2},
+    {"per-window bucket sets, no tables", 0, 3, 3},
+    {"one bucket set over resident window multiples, halving rounds down to ~8 rows per bucket", 2, 3, 3},
+    {"one bucket set over resident window multiples, halving rounds down to ~16 rows per bucket", 2, 4, 3},
+    {"one bucket set over resident window multiples, halving rounds down to ~4 rows per bucket", 2, 2, 3},
+    {"one bucket set over resident window multiples for the G2 vector only (~8 rows), per-window bucket sets for G1", 2, 3, 2},
+    {"one bucket set over resident window multiples for the G1 vectors only (~8 rows), per-window bucket sets for G2", 2, 3, 1},
 };
 constexpr int kNumTunings = (int)(sizeof kTunings / sizeof kTunings[0]);
 }  // namespace
@@ -557,11 +559,21 @@ constexpr int kNumTunings = (int)(sizeof kTunings / sizeof kTunings[0]);
 int bb_tuning_count(void) { return kNumTunings; }
 const char* bb_tuning_name(int index) { return index >= 0 && index < kNumTunings ? kTunings[index].name : nullptr; }
 
+namespace {
+// tables for the vectors of the groups in `groups` (bit 0 = G1, bit 1 = G2); the other vectors lose theirs
+int crs_tables(bb_ctx* ctx, bb_crs* crs, long groups) {
+    for (bb_bases* b : {crs->h, crs->l, crs->a, crs->b_g1, crs->b_g2}) {
+        if (!b) continue;
+        if (groups & (b->group == BB_G1 ? 1 : 2)) BB_TRY(bases_build_table(ctx, b));
+        else bb_bases_drop_table(b);
+    }
+    return BB_OK;
+}
+}  // namespace
+
 int bb_crs_precompute(bb_ctx* ctx, bb_crs* crs) {
     if (!ctx || !crs || crs->ctx != ctx) { set_error("bb_crs_precompute: bad argument"); return BB_ERR_ARG; }
-    for (bb_bases* b : {crs->h, crs->l, crs->a, crs->b_g1, crs->b_g2})
-        if (b) BB_TRY(bases_build_table(ctx, b));
-    return BB_OK;
+    return crs_tables(ctx, crs, 3);
 }
 int bb_crs_drop_tables(bb_crs* crs) {
     if (!crs) { set_error("bb_crs_drop_tables: null argument"); return BB_ERR_ARG; }
@@ -576,9 +588,10 @@ int bb_crs_apply_tuning(bb_ctx* ctx, bb_crs* crs, int index) {
     BB_CUDA(cudaDeviceSynchronize());                  // nothing may still read a table that is about to go
     const Tuning& t = kTunings[index];
     int s = BB_OK;
-    if (t.precompute) s = bb_crs_precompute(ctx, crs);
+    if (t.precompute) s = crs_tables(ctx, crs, t.groups);
     if (s != BB_OK || !t.precompute) bb_crs_drop_tables(crs);
     ctx->opt_msm_precompute = s == BB_OK ? t.precompute : 0;
+    ctx->opt_msm_precompute_groups = s == BB_OK ? t.groups : 3;
     ctx->opt_msm_unified_rows_log = s == BB_OK ? t.rows_log : 3;
     return s;
 }

@@ -79,6 +79,7 @@ void bb_ctx_destroy(bb_ctx* ctx);
  *   msm_precompute     keep window multiples of every base vector resident (see bb_bases_precompute): 1 = one bucket
  *                      array per window, added slot-wise; 2 = ONE bucket array for all windows and halving rounds by its fill
  *   msm_unified_rows_log   msm_precompute = 2: the rounds stop at about 2^this rows per bucket (default 3)
+ *   msm_precompute_groups  which vectors use the tables: mask of 1 (G1) and 2 (G2), default 3
  *   shard_windows      multi-GPU: window groups per base range (default 4; 1 = base ranges only)
  *   ntt_radix8         1 = register radix-8 NTT windows (default 0: measured slower), ntt_tile_log, ntt_col_bits
  *   profile            1 = CUDA-event timing of the MSM stages (bb_profile_read) */
