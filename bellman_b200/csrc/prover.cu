@@ -550,6 +550,7 @@ const Tuning kTunings[] = {
     {"one bucket set over resident window multiples, halving rounds down to ~8 rows per bucket", 2, 3, 3},
     {"one bucket set over resident window multiples, halving rounds down to ~16 rows per bucket", 2, 4, 3},
     {"one bucket set over resident window multiples, halving rounds down to ~4 rows per bucket", 2, 2, 3},
+    {"one bucket set over resident window multiples, halving rounds down to ~32 rows per bucket", 2, 5, 3},
     {"one bucket set over resident window multiples for the G2 vector only (~8 rows), per-window bucket sets for G1", 2, 3, 2},
     {"one bucket set over resident window multiples for the G1 vectors only (~8 rows), per-window bucket sets for G2", 2, 3, 1},
 };
