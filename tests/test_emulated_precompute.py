@@ -103,6 +103,27 @@ def test_emulated_unified_variants(unified):
     G.test_multiexp_error_semantics(unified)
 
 
+def test_emulated_tables_come_and_go(worker):
+    """bb_bases_precompute / bb_bases_drop_table / the option: whichever way the table of a base vector appears or
+    disappears between two MSMs, the point is the same"""
+    n = 300
+    pts = o1.g1_fixed_mul(o1.fr_random(95, n))
+    ex = o1.fr_random(96, n)
+    rc, want = o1.multiexp(1, pts, 0, None, ex)
+    bases = bb.Bases(worker, bb.G1, pts)
+    try:
+        for prepare in (lambda: None, bases.precompute, bases.drop_table,
+                        lambda: worker.set_option("msm_precompute", 2), bases.drop_table,           # rebuilt on first use
+                        lambda: worker.set_option("msm_precompute_groups", 2),                       # G2 only: this G1 table is left alone
+                        bases.drop_table, lambda: worker.set_option("msm_precompute", 1), bases.drop_table):
+            prepare()
+            assert np.array_equal(bb.multiexp(worker, (bases, 0), bb.FullDensity, ex).wait(), want)
+    finally:
+        worker.set_option("msm_precompute", 0)
+        worker.set_option("msm_precompute_groups", 3)
+        bases.free()
+
+
 def test_emulated_unified_deep_rounds(unified):
     G.unified_deep_rounds_case(unified, 1 << 13)            # the rounds chosen by the fill: 8 of them
 
