@@ -424,6 +424,8 @@ def run_prove(args):
     alg_bytes = 128.0 * acc_units
     achieved = alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms > 0 else None
     tr_pair, tr_src = measured_traffic()
+    if tr_src and tuning and tuning["chosen"] != 0:
+        tr_src += " -- captured for the per-window MSM form; the form this run was tuned to has no ncu capture yet"
     pairs_per_launch = acc_units / acc_launches if acc_launches else 0
     line = {
         "metric": METRIC, "value": value, "unit": "constraints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -431,6 +433,8 @@ def run_prove(args):
         "dtype": "u32 limbs (381-bit Fp / 255-bit Fr Montgomery integers)", "data": "synthetic",
         "config": dict(prove_config(log_n, n_constraints, shape["num_aux"], args.witness, f"msm-base-range-shards x{world}, NTT replicated"),
                        crs="[k_i]G, pseudorandom k_i, made on device; witness: valid MiMC-chain assignment",
+                       msm_form=(tuning["name"] + " (measured fastest on this key before the warm-up, see autotune)") if tuning
+                       else ("msm_precompute=%s (forced)" % args.precompute if args.precompute is not None else "per-window bucket sets, no tables (not tuned)"),
                        l2="working set (CRS 430 MB + witness 128 MB at 2^20) exceeds the 126 MB L2; no flush needed",
                        timing="host wall clock over K steps bracketed by device synchronize (+barrier), max over ranks; "
                               "kernel figures by CUDA events on the kernels' own streams"),
