@@ -895,11 +895,11 @@ uint32_t choose_affine_rounds(const bb_ctx* ctx, size_t pairs, uint64_t entries,
     if (ctx->opt_msm_affine_rounds >= 0) return (uint32_t)(ctx->opt_msm_affine_rounds > 8 ? 8 : ctx->opt_msm_affine_rounds);
     if (unified) {
         // one bucket set for all windows: there is one thread per bucket in the XYZZ stage and only D of them, so
-        // the rounds go on until about eight rows per bucket are left (floor(log2 fill) - msm_unified_rows_log, at most 8)
+        // the rounds go on until about eight rows per bucket are left (round(log2 fill) - msm_unified_rows_log, at most 8)
         if (pairs < (1u << 13)) return 0;
         const uint64_t fill = entries / (NB ? NB : 1);
-        uint32_t lg = 0;
-        while ((fill >> (lg + 1)) != 0) lg++;
+        uint32_t lg = 0;                                 // log2 of the fill, rounded to the nearest power of two
+        while (((fill + fill / 2) >> (lg + 1)) != 0) lg++;
         const uint32_t keep = ctx->opt_msm_unified_rows_log < 0 ? 0u : (uint32_t)ctx->opt_msm_unified_rows_log;
         return lg <= keep ? 0u : (lg - keep > 8 ? 8u : lg - keep);
     }
