@@ -33,24 +33,56 @@ void shard_policy(const bb_ctx* ctx, uint32_t idx, uint32_t cnt, uint32_t* b, ui
 }
 
 // scalar multiplication on the host (the five Affine * Fr of prover.rs:326-337 and the two
-// MulAssign<Fr> of :342,351); k is a canonical little-endian 256-bit integer.
-// NOT constant time: the window value indexes the table and a zero window skips its addition, and the XYZZ
-// formulas branch on special cases.  The scalars here are the proof's blinding factors r, s (and r s); the
-// reference multiplies with the bls12_381 crate's constant-time routine.  A deployment that shares the host
-// with untrusted code should keep that property by doing these seven products in its own (Rust) layer and
-// handing the points in -- bb_groth16_finalize_with() takes them as the opaque `static` block.
+// MulAssign<Fr> of :342,351); k is a canonical little-endian 256-bit integer.  The scalars here are the
+// proof's blinding factors r, s (and r s), so the sequence of operations does not depend on them:
+//   * regular signed-digit recoding (Joye-Tunstall): with k made odd, k = 16^64 + sum_{i<64} d_i 16^i where
+//     d_i = (((k >> 4i) | 1) & 31) - 16 is odd and non-zero -- every digit costs four doublings and ONE
+//     addition, none is skipped;
+//   * the table of odd multiples P, 3P, ..., 15P is read in full for every digit and the entry (and its sign) is
+//     selected under a mask -- no secret-dependent address or branch;
+//   * an even k is handled as (k + 1) P - P, both results computed, one selected under a mask.
+// What is left: the XYZZ formulas branch on exceptional operands (identity, P = +-Q), which no digit of a
+// random scalar produces for a point of prime order, and the host field arithmetic ends its products with a
+// data-dependent final subtraction.  (The reference multiplies with the bls12_381 crate's constant-time routine.)
+template <class T>
+void masked_select(T* dst, const T& a, const T& b, uint32_t take_b) {     // take_b = 0 or 0xffffffff
+    static_assert(sizeof(T) % 4 == 0, "whole words");
+    uint32_t wa[sizeof(T) / 4], wb[sizeof(T) / 4];
+    std::memcpy(wa, &a, sizeof(T));
+    std::memcpy(wb, &b, sizeof(T));
+    for (size_t i = 0; i < sizeof(T) / 4; i++) wa[i] = (wa[i] & ~take_b) | (wb[i] & take_b);
+    std::memcpy(dst, wa, sizeof(T));
+}
+
 template <class F>
-XYZZ<F> host_mul(const XYZZ<F>& p, const uint32_t* k) {
-    // 4-bit fixed window
-    XYZZ<F> tab[16];
-    tab[0] = XYZZ<F>::identity();
-    for (int i = 1; i < 16; i++) { tab[i] = tab[i - 1]; tab[i].add(p); }
-    XYZZ<F> acc = XYZZ<F>::identity();
+XYZZ<F> host_mul(const XYZZ<F>& p, const uint32_t* k_in) {
+    uint32_t k[9];
+    const uint32_t even = (~k_in[0]) & 1u;                  // k -> k + 1 when even (no carry out: the low bit is clear)
+    for (int i = 0; i < 8; i++) k[i] = k_in[i];
+    k[0] |= 1u;
+    k[8] = 0;
+    XYZZ<F> tab[8];                                         // (2j + 1) P
+    const XYZZ<F> p2 = p.dbl();
+    tab[0] = p;
+    for (int j = 1; j < 8; j++) { tab[j] = tab[j - 1]; tab[j].add(p2); }
+    XYZZ<F> acc = p;                                        // the leading digit is always 1 (bit 256)
     for (int i = 63; i >= 0; i--) {
         for (int d = 0; d < 4; d++) acc = acc.dbl();
-        uint32_t nib = (k[i / 8] >> (4 * (i % 8))) & 15u;
-        if (nib) acc.add(tab[nib]);
+        const uint32_t pos = 4u * (uint32_t)i, word = pos >> 5, off = pos & 31u;
+        const uint64_t two = (uint64_t)k[word] | ((uint64_t)k[word + 1] << 32);
+        const uint32_t v = ((uint32_t)(two >> off) | 1u) & 31u;          // odd, 1..31; digit = v - 16
+        const uint32_t negative = 0u - (uint32_t)(v < 16u);               // mask
+        const uint32_t mag = ((16u - v) & negative) | ((v - 16u) & ~negative);   // |digit|: odd, 1..15
+        const uint32_t idx = mag >> 1;
+        XYZZ<F> t = tab[0];
+        for (uint32_t j = 1; j < 8; j++) masked_select(&t, t, tab[j], 0u - (uint32_t)(j == idx));
+        const XYZZ<F> tn = t.neg();
+        masked_select(&t, t, tn, negative);
+        acc.add(t);
     }
+    XYZZ<F> minus = acc;
+    minus.add(p.neg());
+    masked_select(&acc, acc, minus, 0u - even);
     return acc;
 }
 

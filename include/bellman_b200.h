@@ -247,8 +247,10 @@ int bb_groth16_finalize(const bb_crs* crs, const uint8_t* partials, size_t count
  * the devices compute the partial sums: finalize_static fills BB_PROOF_STATIC_BYTES opaque bytes,
  * finalize_with consumes them.  bb_groth16_finalize == finalize_static + finalize_with;
  * bb_groth16_prove overlaps them internally.
- * Side channels: the host-side scalar multiplications by r, s and r s are NOT constant time (windowed
- * double-and-add with table lookups); the reference uses bls12_381's constant-time multiplication there. */
+ * Side channels: the host-side scalar multiplications by r, s and r s run a REGULAR ladder -- signed odd digits
+ * (none zero, none skipped), the table read in full under a mask, even scalars as (k + 1) P - P -- so neither the
+ * sequence of operations nor any address depends on the scalar.  Not covered: the field products end with a
+ * data-dependent final subtraction (the reference uses bls12_381's constant-time arithmetic throughout). */
 #define BB_PROOF_STATIC_BYTES 768
 int bb_groth16_finalize_static(const bb_crs* crs, const uint8_t r[32], const uint8_t s[32], uint8_t* static_out);
 int bb_groth16_finalize_with(const bb_crs* crs, const uint8_t* partials, size_t count, const uint8_t r[32],

@@ -27,7 +27,10 @@ def test_point_add_mul_compress_host():
         assert np.array_equal(bb.point_add(group, pts[0:1], zero), pts[0:1])                          # + identity
         neg = mul(pts[0:1], o1.fr_from_ints([R - 1]))
         assert not bb.point_add(group, pts[0:1], neg).any()                                           # P + (-P)
-        for k in (0, 1, 2, R - 1, rng.randrange(R)):
+        # the multiplication is a regular signed-digit ladder (odd digits, even scalars as (k + 1) P - P): digit boundaries,
+        # even / odd, all-ones and sparse scalars
+        for k in [0, 1, 2, 15, 16, 17, 31, 32, 33, R - 1, R - 2, (R - 1) // 2, 1 << 252, (1 << 252) - 1, (1 << 254) + 1,
+                  int("f" * 63, 16), int("8" * 63, 16), int("10" * 31, 16)] + [rng.randrange(R) for _ in range(12)]:
             km = o1.fr_from_ints([k])
             out = np.zeros((1, w), np.uint64)
             assert lib.bb_point_mul(C.c_int(group), pts[2:3].ctypes.data_as(C.c_void_p), km.ctypes.data_as(C.c_void_p),
@@ -37,6 +40,10 @@ def test_point_add_mul_compress_host():
             assert lib.bb_point_mul(C.c_int(group), pts[2:3].ctypes.data_as(C.c_void_p), kc.ctypes.data_as(C.c_void_p),
                                     C.c_int(bb.FORM_CANONICAL), out.ctypes.data_as(C.c_void_p)) == 0
             assert np.array_equal(out, mul(pts[2:3], km)), k
+        out = np.ones((1, w), np.uint64)                                                              # k * identity = identity
+        km = o1.fr_from_ints([rng.randrange(R)])
+        assert lib.bb_point_mul(C.c_int(group), zero.ctypes.data_as(C.c_void_p), km.ctypes.data_as(C.c_void_p),
+                                C.c_int(bb.FORM_MONTGOMERY), out.ctypes.data_as(C.c_void_p)) == 0 and not out.any()
         want = comp(pts)
         for i in range(len(ks)):
             assert bb.point_compress(group, pts[i:i + 1]) == bytes(want[i])
