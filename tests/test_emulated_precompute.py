@@ -49,12 +49,30 @@ def test_emulated_precompute_variants(precompute):
 
 
 def test_emulated_precompute_prove_and_shards(precompute):
-    E.test_emulated_prove_mimc322_and_shards(precompute)
+    """a 2^7-constraint MiMC proof and its 2-way shards over per-window-slot tables (the 322-round proof and the 8-way
+    shards run under the one-bucket-set form below)"""
+    import random
+    rng = random.Random(72)
+    mc = o1.Mimc(60, seed=4)
+    mc.set_toxic([rng.randrange(1, o1.FR_MODULUS) for _ in range(5)])
+    mc.generate()
+    params = bb.Parameters(precompute, mc.export_params())
+    asg = G._assignment(mc.witness())
+    r, s = rng.randrange(o1.FR_MODULUS), rng.randrange(o1.FR_MODULUS)
+    proof = bb.create_proof(asg, params, r, s)
+    assert proof == mc.prove(r, s) == mc.expected_proof(r, s)
+    parts = []
+    for k in range(2):
+        pk = bb.Parameters(precompute, mc.export_params(), shard_index=k, shard_count=2)
+        parts.append(bb.prove_partials(asg, pk))
+        pk.free()
+    assert bb.finalize(params, parts, r, s) == proof
 
 
-@pytest.mark.parametrize("variant", [11, 22, 33, 44, 4, 30])
+@pytest.mark.parametrize("variant", [33])
 def test_emulated_accumulate_variants(worker, variant):
-    """msm_acc_variant = g1 + 10 * g2: 1, 2, 4 = launch-bound variants (4 / 5 / 3 CTAs per SM), 3 = next base prefetched during the addition"""
+    """msm_acc_variant: round 1's launch-bound / prefetch variants of the accumulate kernel were measured (no gain) and removed;
+    the key is still accepted and changes nothing"""
     worker.set_option("msm_acc_variant", variant)
     try:
         for pre in (0, 1):
