@@ -128,8 +128,9 @@ void bb_bases_free(bb_bases* b);
 /* Builds the table of window multiples 2^(c w) P_i of a resident base vector (c chosen from its
  * length).  MSMs over these bases then accumulate every window into one bucket set: one summation
  * by parts and no Horner fold instead of one per window (multiexp.rs:271-300), at (windows x) the
- * base storage.  Results are unchanged.  With bb_ctx_set_option(ctx, "msm_precompute", 1) the table
- * is built on first use instead. */
+ * base storage.  Results are unchanged.  With bb_ctx_set_option(ctx, "msm_precompute", 1 or 2) the table
+ * is built on first use instead; 2 also sorts the digits of all windows into ONE bucket array (deeper halving
+ * rounds, a sixteenth of the bucket reduction) -- the form bb_groth16_autotune measures against the default. */
 int bb_bases_precompute(bb_ctx* ctx, bb_bases* bases);
 /* Frees that table again.  No MSM over these bases may be in flight. */
 int bb_bases_drop_table(bb_bases* bases);
