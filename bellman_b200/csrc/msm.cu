@@ -1033,7 +1033,10 @@ int launch_msm(bb_msm_job* job) {
     // about the mean load (at least 32 entries, and few enough that <= ~1M tasks can exist), so
     // the serial chain any thread owns stays short and the task sums are merged by a tree.
     const uint64_t rows = slots >> R;                 // what the XYZZ stage walks
-    const uint64_t avg = (rows + NB - 1) / NB;
+    // deep buckets without halving rounds (few buckets: a small window, or one bucket set under a short job) must not
+    // become one long serial chain per thread either: above 64 rows per bucket every bucket is cut into tasks of 64
+    const uint64_t avg_raw = (rows + NB - 1) / NB;
+    const uint64_t avg = avg_raw > 64 ? 64 : avg_raw;
     uint64_t cap64 = 4 * avg < 64 ? 64 : 4 * avg;
     uint64_t len64 = avg < 32 ? 32 : avg;
     if (len64 < (rows + 1048575) / 1048576) len64 = (rows + 1048575) / 1048576;
