@@ -204,7 +204,8 @@ class Bases:
 
     def free(self):
         if getattr(self, "_h", None):
-            load_library().bb_bases_free(self._h)
+            if getattr(self.worker, "_h", None):     # a context that is already gone took the device memory with it
+                load_library().bb_bases_free(self._h)
             self._h = None
 
     def __del__(self):
@@ -476,7 +477,8 @@ class Parameters:
 
     def free(self):
         if getattr(self, "_h", None):
-            load_library().bb_crs_destroy(self._h)
+            if getattr(self.worker, "_h", None):     # (the garbage collector may finalise a Worker before its children)
+                load_library().bb_crs_destroy(self._h)
             self._h = None
 
     def __del__(self):
