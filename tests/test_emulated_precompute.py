@@ -154,3 +154,58 @@ def test_emulated_unified_prove_and_shards(unified):
 def test_emulated_autotune(worker):
     G.autotune_case(worker, 60)
     assert bb.load_library().bb_tuning_name(99) is None
+
+
+def test_emulated_table_forms_fuzz(worker):
+    """Random small MSMs under the table forms -- form 1 / 2, group mask, forced or fill-chosen rounds, pairs per thread,
+    stop of the rounds, window size, task splitting, density, offset, missing and identity bases, 0 / 1 / small / negative
+    scalars, scalar form -- against the oracle, including which SynthesisError comes back.  (1200 seeds of this generator
+    ran clean when the one-bucket-set form was written.)"""
+    import random
+    R = o1.FR_MODULUS
+    errs = {2: bb.UnexpectedIdentity, 3: bb.IoError}
+    pool1 = o1.g1_fixed_mul(o1.fr_random(7, 400))
+    pool2 = o1.g2_fixed_mul(o1.fr_random(8, 120))
+    keys = ("msm_window_bits", "msm_big_cap", "msm_precompute", "msm_affine_rounds")
+    try:
+        for case in range(45):
+            rng = random.Random(case)
+            group = 1 if rng.random() < 0.75 else 2
+            pool = pool1 if group == 1 else pool2
+            n = rng.choice([0, 1, 2, 3, 5, 17, 31, 32, 33, 64, 65, 100, 150, 400]) if group == 1 else rng.choice([0, 1, 2, 7, 33, 60])
+            dens = None
+            if rng.random() < 0.6:
+                p_set = rng.choice([0.1, 0.5, 0.9, 1.0])
+                dens = np.array([rng.random() < p_set for _ in range(n)], dtype=bool)
+            k = n if dens is None else int(dens.sum())
+            off = rng.choice([0, 0, 1, 5, 20])
+            nb = max(0, off + k + rng.choice([0, 0, 0, 3, -1, -2]))          # negative slack: the source runs dry
+            bases = pool[[rng.randrange(pool.shape[0]) for _ in range(nb)]].copy().reshape(nb, pool.shape[1])
+            for j in range(nb):
+                if rng.random() < 0.04:
+                    bases[j] = 0                                              # identity base
+            vals = [rng.choice([rng.randrange(R), rng.randrange(R), 0, 1, rng.randrange(300), R - 1, (1 << 254) + rng.randrange(1 << 20)]) % R
+                    for _ in range(n)]
+            ex = o1.fr_from_ints(vals) if n else np.zeros((0, 4), np.uint64)
+            worker.set_option("msm_window_bits", rng.choice([0, 0, 2, 3, 4, 7, 8, 11, 13]))
+            worker.set_option("msm_big_cap", rng.choice([0, 0, 2, 5]))
+            worker.set_option("msm_precompute", rng.choice([2, 2, 2, 1]))
+            worker.set_option("msm_precompute_groups", rng.choice([3, 3, 1, 2]))
+            worker.set_option("msm_affine_rounds", rng.choice([-1, -1, 0, 1, 2, 3, 5, 8]))
+            worker.set_option("msm_affine_batch", rng.choice([16, 16, 1, 3, 7]))
+            worker.set_option("msm_unified_rows_log", rng.choice([3, 0, 2, 5]))
+            rc, want = o1.multiexp(group, bases, off, None if dens is None else dens.astype(np.uint8), ex)
+            form = rng.choice([bb.FORM_MONTGOMERY, bb.FORM_CANONICAL])
+            sc = ex if form == bb.FORM_MONTGOMERY else o1.fr_to_canonical(ex)
+            dm = bb.FullDensity if dens is None else bb.DensityTracker(dens)
+            try:
+                got = bb.multiexp(worker, (bb.Bases(worker, bb.G1 if group == 1 else bb.G2, bases), off), dm, sc, form).wait()
+                assert rc == 0 and np.array_equal(got, want), case
+            except bb.SynthesisError as e:
+                assert rc in errs and isinstance(e, errs[rc]), (case, rc, e)
+    finally:
+        for key in keys:
+            worker.set_option(key, -1 if key == "msm_affine_rounds" else 0)
+        worker.set_option("msm_precompute_groups", 3)
+        worker.set_option("msm_affine_batch", 16)
+        worker.set_option("msm_unified_rows_log", 3)
