@@ -79,8 +79,22 @@ def autotune_sharded(assignment, params, r, s, device_ptrs=None, reps=3, group=N
         if _all_reduce(ok, "MIN", group) < 1.0:
             ms.append(-1.0)
             continue
+        def prove():
+            """one sharded proof; every rank learns whether ANY rank failed (rank 0 alone can fail in finalize), so that
+            all ranks leave this form together and the collectives below stay matched"""
+            proof, err = None, None
+            try:
+                proof = create_proof_sharded(assignment, params, params, r, s, device_ptrs, group, split_h)
+                params.worker.synchronize()
+            except (BackendError, SynthesisError, AssertionError) as e:
+                err = e
+            done = time.perf_counter()                   # the status exchange below is not part of the proof
+            if _all_reduce(1.0 if err else 0.0, "MAX", group) > 0.0:
+                raise err if err is not None else BackendError("the sharded proof failed on another rank")
+            return proof, done
+
         try:
-            proof = create_proof_sharded(assignment, params, params, r, s, device_ptrs, group, split_h)      # raises on every rank or on none
+            proof, _ = prove()
             same = 1.0
             if rank == 0:
                 if index == 0:
@@ -94,9 +108,8 @@ def autotune_sharded(assignment, params, r, s, device_ptrs=None, reps=3, group=N
                 params.worker.synchronize()
                 dist.barrier(group)
                 t0 = time.perf_counter()
-                create_proof_sharded(assignment, params, params, r, s, device_ptrs, group, split_h)
-                params.worker.synchronize()
-                dt = _all_reduce(time.perf_counter() - t0, "MAX", group)
+                _, t1 = prove()
+                dt = _all_reduce(t1 - t0, "MAX", group)
                 best = dt if best is None or dt < best else best
             ms.append(round(1e3 * best, 3))
         except (BackendError, SynthesisError, AssertionError):
