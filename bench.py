@@ -47,6 +47,7 @@ def parse():
                                                                    "per window, 2 = window multiples + ONE bucket array) instead of measuring")
     ap.add_argument("--autotune", type=int, default=1, help="1 = before the warm-up, time every MSM form on this key (bb_groth16_autotune; sharded: the whole "
                                                             "sharded proof, max over ranks) and run the fastest whose results are byte-identical; 0 = default form")
+    ap.add_argument("--autotune-reps", type=int, default=3, help="timed proofs per MSM form in the tuner (after one checked proof)")
     ap.add_argument("--acc-variant", type=int, default=0)
     ap.add_argument("--ntt-radix8", type=int, default=0, help="1 = register radix-8 windows (k_ntt_pass8) instead of radix-2 sweeps in shared memory (k_ntt_pass)")
     ap.add_argument("--reduce-2d", type=int, default=1, help="0 = serial running-sum recursion over whole windows instead of row/column sums first")
@@ -337,12 +338,12 @@ def run_prove(args):
     if args.autotune and args.precompute is None and args.affine_rounds < 0:
         log("measuring the MSM forms on this key (autotune)")
         if world == 1:
-            tuning = params.autotune(asg, reps=3, device_ptrs=dev)
+            tuning = params.autotune(asg, reps=args.autotune_reps, device_ptrs=dev)
         else:
             from bellman_b200.distributed import autotune_sharded
-            tuning = autotune_sharded(asg, params, r, s, device_ptrs=dev, reps=3)
+            tuning = autotune_sharded(asg, params, r, s, device_ptrs=dev, reps=args.autotune_reps)
         tuning["forms"] = bb.tuning_names()
-        tuning["note"] = ("ms per proof and form, fastest of 3 after one checked proof (negative: -1 tables do not fit, -2 failed, "
+        tuning["note"] = (f"ms per proof and form, fastest of {args.autotune_reps} after one checked proof (negative: -1 tables do not fit, -2 failed, "
                           "-3 results differ: never eligible); measured before the warm-up, outside the timed regions")
         log(f"autotune: {tuning['ms']} ms -> form {tuning['chosen']}: {tuning['name']}")
 

@@ -55,7 +55,7 @@ bb.LIB_PATH, bb._lib = EMU_LIB, None          # the product sources on host fibe
 spec = importlib.util.spec_from_file_location("bench", ROOT + "/bench.py")
 bench = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(bench)
-sys.argv = ["bench.py", "--log-size", "8", "--steps", "2", "--warmup", "1", "--cpu-sample-log", "8"] + EXTRA
+sys.argv = ["bench.py", "--log-size", "8", "--steps", "2", "--warmup", "1", "--cpu-sample-log", "8", "--autotune-reps", "1"] + EXTRA
 bench.main()
 '''
 

@@ -152,7 +152,7 @@ def test_emulated_unified_prove_and_shards(unified):
 
 
 def test_emulated_autotune(worker):
-    G.autotune_case(worker, 60)
+    G.autotune_case(worker, 60, reps=1)
     assert bb.load_library().bb_tuning_name(99) is None
 
 

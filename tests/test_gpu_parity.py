@@ -946,7 +946,7 @@ def test_unified_prove_2e20(unified):
     test_prove_synthetic_chain_trapdoor(unified, 524287)
 
 
-def autotune_case(worker, rounds):
+def autotune_case(worker, rounds, reps=2):
     """bb_groth16_autotune: every MSM form proves the same witness, only forms with the default form's partial sums
     are eligible, the key is left configured for the chosen one and proves to the expected bytes"""
     rng = random.Random(rounds + 1)
@@ -956,7 +956,7 @@ def autotune_case(worker, rounds):
     params = bb.Parameters(worker, mc.export_params())
     asg = _assignment(mc.witness())
     try:
-        rep = params.autotune(asg, reps=2)
+        rep = params.autotune(asg, reps=reps)
         names = bb.tuning_names()
         assert len(rep["ms"]) == len(names) >= 2 and 0 <= rep["chosen"] < len(names) and rep["name"] == names[rep["chosen"]]
         assert rep["ms"][0] > 0 and rep["ms"][rep["chosen"]] > 0
