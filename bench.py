@@ -46,7 +46,10 @@ def parse():
     ap.add_argument("--precompute", type=int, default=None, help="force msm_precompute (0 = per-window bucket sets, 1 = window multiples + one bucket array "
                                                                    "per window, 2 = window multiples + ONE bucket array) instead of measuring")
     ap.add_argument("--autotune", type=int, default=1, help="1 = before the warm-up, time every MSM form on this key (bb_groth16_autotune; sharded: the whole "
-                                                            "sharded proof, max over ranks) and run the fastest whose results are byte-identical; 0 = default form")
+                                                            "sharded proof, max over ranks) and run the fastest whose results are byte-identical; at N = 1 the tuner "
+                                                            "runs in a child process (a form that faults there cannot take the measurement down with it); "
+                                                            "2 = the same in this process; 0 = default form")
+    ap.add_argument("--tune-child", action="store_true", help="internal: build the same key and witness, run the tuner, print its report, exit")
     ap.add_argument("--autotune-reps", type=int, default=3, help="timed proofs per MSM form in the tuner (after one checked proof)")
     ap.add_argument("--acc-variant", type=int, default=0)
     ap.add_argument("--ntt-radix8", type=int, default=0, help="1 = register radix-8 windows (k_ntt_pass8) instead of radix-2 sweeps in shared memory (k_ntt_pass)")
@@ -263,6 +266,28 @@ def run_reference(args):
     emit(line)
 
 
+def tune_in_child(args, log_n):
+    """The per-key tuner (bb_groth16_autotune) in a child process that builds the same synthetic key and witness: its
+    report names the fastest eligible MSM form, which the parent then selects with bb_crs_apply_tuning.  Whatever happens
+    to the child -- a CUDA fault in a form that has never run on this machine included -- the parent's context and its
+    measurement are untouched and it stays on the default form."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--tune-child", "--log-size", str(log_n), "--witness", args.witness,
+           "--autotune-reps", str(args.autotune_reps), "--window-bits", str(args.window_bits), "--reduce-k", str(args.reduce_k),
+           "--reduce-k1", str(args.reduce_k1), "--reduce-2d", str(args.reduce_2d), "--affine-tma", str(args.affine_tma),
+           "--ntt-radix8", str(args.ntt_radix8), "--affine-batch", str(args.affine_batch)]
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        lines = [l for l in res.stdout.splitlines() if l.strip().startswith("{")]
+        if res.returncode != 0 or not lines:
+            tail = " | ".join((res.stderr or "").strip().splitlines()[-3:])
+            return {"chosen": 0, "ms": None, "error": f"rc {res.returncode}: {tail[-400:]}"}
+        rep = json.loads(lines[-1])["tune_child"]
+        rep["error"] = None
+        return rep
+    except Exception as e:                               # timeout, unparsable report, ...
+        return {"chosen": 0, "ms": None, "error": f"{type(e).__name__}: {e}"[:400]}
+
+
 def prove_config(log_n, constraints, num_aux, witness, parallelism):
     """`config` of the prove workload: identical keys and values in both arms."""
     half = (constraints // 2) - 1 + 1
@@ -335,17 +360,32 @@ def run_prove(args):
     # device (N > 1: the sharded proof, max over ranks), only forms whose results are byte-identical to the default's are
     # eligible, the fastest stays configured.  Outside every timed region; the timed steps run the chosen form only.
     tuning = None
+    if args.tune_child:                                  # the sandboxed tuner of a parent bench.py (same key, same witness)
+        rep = params.autotune(asg, reps=args.autotune_reps, device_ptrs=dev)
+        emit({"tune_child": rep})
+        worker.close()
+        return
+    proof_default = None
     if args.autotune and args.precompute is None and args.affine_rounds < 0:
         log("measuring the MSM forms on this key (autotune)")
-        if world == 1:
+        if world == 1 and args.autotune == 1:
+            proof_default = bb.create_proof(asg, params, r, s, dev)          # default form, for the byte comparison after the timed legs
+            tuning = tune_in_child(args, log_n)
+            if tuning.get("error") is None:
+                params.apply_tuning(tuning["chosen"])
+            else:
+                log(f"tuner process failed, staying on the default form: {tuning['error']}")
+        elif world == 1:
             tuning = params.autotune(asg, reps=args.autotune_reps, device_ptrs=dev)
         else:
             from bellman_b200.distributed import autotune_sharded
             tuning = autotune_sharded(asg, params, r, s, device_ptrs=dev, reps=args.autotune_reps)
         tuning["forms"] = bb.tuning_names()
+        tuning.setdefault("name", tuning["forms"][tuning["chosen"]])
+        tuning["where"] = "child process" if (world == 1 and args.autotune == 1) else "in process"
         tuning["note"] = (f"ms per proof and form, fastest of {args.autotune_reps} after one checked proof (negative: -1 tables do not fit, -2 failed, "
                           "-3 results differ: never eligible); measured before the warm-up, outside the timed regions")
-        log(f"autotune: {tuning['ms']} ms -> form {tuning['chosen']}: {tuning['name']}")
+        log(f"autotune: {tuning.get('ms')} ms -> form {tuning['chosen']}: {tuning['name']}")
 
     def step(device_ptrs):
         if world == 1:
@@ -405,6 +445,7 @@ def run_prove(args):
     proof_single = None
     if rank == 0:
         assert proof_val == proof_e2e and len(proof_val) == 192
+        assert proof_default is None or proof_default == proof_val, "the tuned MSM form changed the proof bytes"
         if world > 1:
             # the N-GPU proof must be the single-GPU proof: rank 0 proves once more over an unsharded copy of the
             # same synthetic CRS (outside every timed region) and compares the bytes
@@ -434,7 +475,8 @@ def run_prove(args):
         "dtype": "u32 limbs (381-bit Fp / 255-bit Fr Montgomery integers)", "data": "synthetic",
         "config": dict(prove_config(log_n, n_constraints, shape["num_aux"], args.witness, f"msm-base-range-shards x{world}, NTT replicated"),
                        crs="[k_i]G, pseudorandom k_i, made on device; witness: valid MiMC-chain assignment",
-                       msm_form=(tuning["name"] + " (measured fastest on this key before the warm-up, see autotune)") if tuning
+                       msm_form=("per-window bucket sets, no tables (the tuner process failed, see autotune.error)" if tuning and tuning.get("error")
+                                 else tuning["name"] + " (measured fastest on this key before the warm-up, see autotune)") if tuning
                        else ("msm_precompute=%s (forced)" % args.precompute if args.precompute is not None else "per-window bucket sets, no tables (not tuned)"),
                        l2="working set (CRS 430 MB + witness 128 MB at 2^20) exceeds the 126 MB L2; no flush needed",
                        timing="host wall clock over K steps bracketed by device synchronize (+barrier), max over ranks; "

@@ -55,7 +55,7 @@ bb.LIB_PATH, bb._lib = EMU_LIB, None          # the product sources on host fibe
 spec = importlib.util.spec_from_file_location("bench", ROOT + "/bench.py")
 bench = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(bench)
-sys.argv = ["bench.py", "--log-size", "8", "--steps", "2", "--warmup", "1", "--cpu-sample-log", "8", "--autotune-reps", "1"] + EXTRA
+sys.argv = ["bench.py", "--log-size", "8", "--steps", "2", "--warmup", "1", "--cpu-sample-log", "8", "--autotune-reps", "1", "--autotune", "2"] + EXTRA
 bench.main()
 '''
 
@@ -83,6 +83,26 @@ def test_own_arm_dry_run_on_the_emulated_device(tmp_path, emu_lib):
     assert "workload" in d["config"] and "model" not in d["config"]
     at = d["autotune"]                                  # the MSM form was measured before the warm-up; every form eligible here
     assert len(at["ms"]) == len(at["forms"]) >= 2 and all(t > 0 for t in at["ms"]) and at["ms"][at["chosen"]] == min(at["ms"])
+
+
+def test_tuner_child_mode_and_parent_fallback(tmp_path, emu_lib):
+    """bench.py's sandboxed tuner: (1) child mode (--tune-child) builds the key and witness, tunes and prints its report --
+    run here on the emulated device; (2) a parent whose child cannot run (the real library finds no CUDA device in this
+    container) records the error and measures the default form."""
+    script = tmp_path / "child.py"
+    script.write_text(f"ROOT = {ROOT!r}\nEMU_LIB = {emu_lib!r}\nEXTRA = ['--tune-child']\n" + DRY_RUN)
+    res = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-3000:]
+    rep = json.loads([l for l in res.stdout.splitlines() if l.strip()][-1])["tune_child"]
+    assert all(t > 0 for t in rep["ms"]) and rep["ms"][rep["chosen"]] == min(rep["ms"]) and rep["name"]
+    script = tmp_path / "parent.py"
+    script.write_text(f"ROOT = {ROOT!r}\nEMU_LIB = {emu_lib!r}\nEXTRA = ['--autotune', '1', '--no-cpu-baseline']\n" + DRY_RUN)
+    res = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-3000:]
+    d = json.loads([l for l in res.stdout.splitlines() if l.strip()][-1])
+    at = d["autotune"]
+    assert at["error"] and at["chosen"] == 0 and at["where"] == "child process" and "tuner process failed" in d["config"]["msm_form"]
+    assert d["value"] > 0 and d["gpu_launches"] > 100
 
 
 def test_msm_microbench_dry_run_on_the_emulated_device(tmp_path, emu_lib):
