@@ -466,7 +466,9 @@ class Parameters:
 
     def autotune(self, assignment, reps=3, device_ptrs=None):
         """bb_groth16_autotune: prove `assignment` with every MSM form, keep the fastest whose partial sums equal the
-        default form's.  Returns {"chosen": index, "name": ..., "ms": [per form; negative = not eligible]}."""
+        default form's.  Returns {"chosen": index, "name": ..., "ms": [per form; negative = not eligible]}.
+        A sharded key (shard_count > 1) is only measured and stays on the default form: all shards must run the same
+        form (see distributed.autotune_sharded)."""
         lib = load_library()
         n = lib.bb_tuning_count()
         ms = (C.c_double * n)()

@@ -1180,7 +1180,9 @@ int msm_start(bb_ctx* ctx, const bb_bases* bases, size_t base_offset, const uint
     const bool tables_wanted = ctx->opt_msm_precompute && (ctx->opt_msm_precompute_groups & (bases->group == BB_G1 ? 1 : 2));
     if (tables_wanted && bases->n && !bases->d_table) {
         int ts = bases_build_table(ctx, const_cast<bb_bases*>(bases));     // first use; bb_bases_precompute does it up front
-        if (ts != BB_OK && ts != BB_ERR_OOM) { job->status = ts; return BB_OK; }   // no room for the table: the per-window path needs none
+        // no room for the table: the per-window path needs none -- but only a whole key may fall back by itself: the shards
+        // of a window-sharded key must all cut the scalars into the same windows
+        if (ts != BB_OK && !(ts == BB_ERR_OOM && bases->win_count <= 1)) { job->status = ts; return BB_OK; }
     }
     job->precomp = bases->d_table != nullptr && (tables_wanted || !ctx->opt_msm_precompute);   // a table built by hand (bb_bases_precompute) is used as it is
     job->unified = job->precomp && ctx->opt_msm_precompute >= 2;

@@ -641,6 +641,12 @@ int bb_groth16_autotune(bb_ctx* ctx, bb_crs* crs, const bb_witness* w, int reps,
     uint8_t ref[BB_PARTIALS_BYTES], got[BB_PARTIALS_BYTES];
     double ms[kNumTunings];
     int best = 0;
+    // A shard of a window-sharded key owns the windows w = index mod count of its base range, and the window size differs
+    // between the forms (the table forms take it from the vector, the default from the job): the (base, window) pairs a
+    // shard sums -- and with them its partial sums -- are comparable only after all shards are added up.  For a sharded
+    // key this call therefore only MEASURES (every form must still prove without an error) and leaves the default form
+    // configured: all shards must run the same form, which is a collective decision (distributed.autotune_sharded).
+    const bool whole_key = crs->shard_count == 1;
     for (int i = 0; i < kNumTunings; i++) {
         ms[i] = -1.0;                                   // -1: not available here (the tables do not fit)
         int s = bb_crs_apply_tuning(ctx, crs, i);
@@ -653,7 +659,7 @@ int bb_groth16_autotune(bb_ctx* ctx, bb_crs* crs, const bb_witness* w, int reps,
             continue;
         }
         if (i == 0) std::memcpy(ref, got, sizeof ref);
-        else if (std::memcmp(ref, got, sizeof ref) != 0) { ms[i] = -3.0; continue; }     // -3: different partial sums -- never eligible
+        else if (whole_key && std::memcmp(ref, got, sizeof ref) != 0) { ms[i] = -3.0; continue; }     // -3: different partial sums -- never eligible
         double fastest = 1e300;
         for (int k = 0; k < reps && s == BB_OK; k++) {
             const auto t0 = std::chrono::steady_clock::now();
@@ -667,7 +673,7 @@ int bb_groth16_autotune(bb_ctx* ctx, bb_crs* crs, const bb_witness* w, int reps,
     }
     if (ms_out) for (int i = 0; i < kNumTunings; i++) ms_out[i] = ms[i];
     if (chosen) *chosen = best;
-    return bb_crs_apply_tuning(ctx, crs, best);
+    return bb_crs_apply_tuning(ctx, crs, whole_key ? best : 0);
 }
 
 int bb_groth16_prove(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w, const uint8_t* r_bytes, const uint8_t* s_bytes, uint8_t* proof) {

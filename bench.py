@@ -50,6 +50,8 @@ def parse():
                                                             "runs in a child process (a form that faults there cannot take the measurement down with it); "
                                                             "2 = the same in this process; 0 = default form")
     ap.add_argument("--tune-child", action="store_true", help="internal: build the same key and witness, run the tuner, print its report, exit")
+    ap.add_argument("--shard-index", type=int, default=0, help="internal (--tune-child): the key shard of the parent rank")
+    ap.add_argument("--shard-count", type=int, default=1)
     ap.add_argument("--autotune-reps", type=int, default=3, help="timed proofs per MSM form in the tuner (after one checked proof)")
     ap.add_argument("--acc-variant", type=int, default=0)
     ap.add_argument("--ntt-radix8", type=int, default=0, help="1 = register radix-8 windows (k_ntt_pass8) instead of radix-2 sweeps in shared memory (k_ntt_pass)")
@@ -266,13 +268,14 @@ def run_reference(args):
     emit(line)
 
 
-def tune_in_child(args, log_n):
+def tune_in_child(args, log_n, shard=(0, 1), reps=None):
     """The per-key tuner (bb_groth16_autotune) in a child process that builds the same synthetic key and witness: its
     report names the fastest eligible MSM form, which the parent then selects with bb_crs_apply_tuning.  Whatever happens
     to the child -- a CUDA fault in a form that has never run on this machine included -- the parent's context and its
     measurement are untouched and it stays on the default form."""
     cmd = [sys.executable, os.path.abspath(__file__), "--tune-child", "--log-size", str(log_n), "--witness", args.witness,
-           "--autotune-reps", str(args.autotune_reps), "--window-bits", str(args.window_bits), "--reduce-k", str(args.reduce_k),
+           "--autotune-reps", str(reps or args.autotune_reps), "--shard-index", str(shard[0]), "--shard-count", str(shard[1]),
+           "--window-bits", str(args.window_bits), "--reduce-k", str(args.reduce_k),
            "--reduce-k1", str(args.reduce_k1), "--reduce-2d", str(args.reduce_2d), "--affine-tma", str(args.affine_tma),
            "--ntt-radix8", str(args.ntt_radix8), "--affine-batch", str(args.affine_batch)]
     try:
@@ -286,6 +289,25 @@ def tune_in_child(args, log_n):
         return rep
     except Exception as e:                               # timeout, unparsable report, ...
         return {"chosen": 0, "ms": None, "error": f"{type(e).__name__}: {e}"[:400]}
+
+
+def tune_sharded_gated(args, log_n, rank, world, asg, params, r, s, dev):
+    """The collective tuner (distributed.autotune_sharded) behind a gate: with --autotune 1 every rank first lets a child
+    process tune its own key shard (all forms, on the shapes of the sharded proof's MSMs); only if every rank's child
+    survives does the collective tuner run inside the ranks.  Otherwise every rank stays on the default form."""
+    from bellman_b200.distributed import _all_reduce, autotune_sharded
+    probe_error = None
+    if args.autotune == 1:
+        probe = tune_in_child(args, log_n, shard=(rank, world), reps=1)
+        mine = probe.get("error")
+        if _all_reduce(0.0 if mine is None else 1.0, "MAX") > 0.0:
+            probe_error = mine or "the tuner child of another rank failed"
+    if probe_error is None:
+        tuning = autotune_sharded(asg, params, r, s, device_ptrs=dev, reps=args.autotune_reps)
+        tuning["error"] = None
+        return tuning
+    log(f"tuner gate failed, staying on the default form: {probe_error}")
+    return {"chosen": 0, "ms": None, "error": probe_error}
 
 
 def prove_config(log_n, constraints, num_aux, witness, parallelism):
@@ -310,7 +332,11 @@ def run_prove(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
+    shard = (rank, world)
+    if args.tune_child:                                  # a parent rank's sandboxed tuner: one process, that rank's GPU and key shard
+        shard = (args.shard_index, args.shard_count)
+        world, rank = 1, 0
+    elif world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run for --gpus > 1")
     torch.cuda.set_device(local)
@@ -343,7 +369,7 @@ def run_prove(args):
         asg.aux_assignment[1::4] = 0
         asg.aux_assignment[3::4] = one
     log("generating the synthetic CRS on the device")
-    params = bb.Parameters.synthetic(worker, 21, shape, shard_index=rank, shard_count=world)
+    params = bb.Parameters.synthetic(worker, 21, shape, shard_index=shard[0], shard_count=shard[1])
     log("CRS resident")
     r, s = 0x1234567 % FR_MODULUS, 0x7654321 % FR_MODULUS
 
@@ -378,11 +404,10 @@ def run_prove(args):
         elif world == 1:
             tuning = params.autotune(asg, reps=args.autotune_reps, device_ptrs=dev)
         else:
-            from bellman_b200.distributed import autotune_sharded
-            tuning = autotune_sharded(asg, params, r, s, device_ptrs=dev, reps=args.autotune_reps)
+            tuning = tune_sharded_gated(args, log_n, rank, world, asg, params, r, s, dev)
         tuning["forms"] = bb.tuning_names()
         tuning.setdefault("name", tuning["forms"][tuning["chosen"]])
-        tuning["where"] = "child process" if (world == 1 and args.autotune == 1) else "in process"
+        tuning["where"] = ("child process" if world == 1 else "in the ranks, after every rank's child process survived all forms") if args.autotune == 1 else "in process"
         tuning["note"] = (f"ms per proof and form, fastest of {args.autotune_reps} after one checked proof (negative: -1 tables do not fit, -2 failed, "
                           "-3 results differ: never eligible); measured before the warm-up, outside the timed regions")
         log(f"autotune: {tuning.get('ms')} ms -> form {tuning['chosen']}: {tuning['name']}")

@@ -272,8 +272,12 @@ int bb_groth16_prove(bb_ctx* ctx, const bb_crs* crs, const bb_witness* w,
  * fastest taken), admits a form only if its 960 bytes of partial sums equal the default form's, leaves the context
  * and the key configured for the fastest one and frees the tables if they lost.  ms_out (bb_tuning_count()
  * doubles, may be NULL): milliseconds per form; -1 = not available (no room for the tables), -2 = failed,
- * -3 = different partial sums.  *chosen = index of the form now active.  bb_crs_apply_tuning selects a form by
- * hand (multi-GPU callers time the sharded proof themselves and agree on one index).  Form 0 is the default. */
+ * -3 = different partial sums.  *chosen = index of the fastest eligible form, which is now active.
+ * Sharded keys: all shards MUST run the same form (the forms cut the scalars into windows of different sizes, so a
+ * shard's (base, window) pairs -- and its partial sums -- depend on the form; only the sum over all shards does not).
+ * For a key with shard_count > 1 this call therefore only measures (no comparison, *chosen = the fastest form here)
+ * and leaves the DEFAULT form active; the shards agree on one index -- time the whole sharded proof, compare the
+ * final proof bytes -- and each selects it with bb_crs_apply_tuning.  Form 0 is the default. */
 int bb_tuning_count(void);
 const char* bb_tuning_name(int index);
 int bb_crs_apply_tuning(bb_ctx* ctx, bb_crs* crs, int index);

@@ -154,6 +154,23 @@ def test_emulated_unified_prove_and_shards(unified):
 def test_emulated_autotune(worker):
     G.autotune_case(worker, 60, reps=1)
     assert bb.load_library().bb_tuning_name(99) is None
+    # one shard of a window-sharded key: its partial sums depend on the form (the forms cut the scalars into windows of
+    # different sizes), so the single-process tuner only measures it and leaves the default form active
+    asg, shape = bb.synth_mimc(63, seed=20)
+    whole = bb.Parameters.synthetic(worker, 21, shape)
+    proof = bb.create_proof(asg, whole, 5, 7)
+    shards = [bb.Parameters.synthetic(worker, 21, shape, shard_index=k, shard_count=2) for k in range(2)]
+    default_parts = [bb.prove_partials(asg, p) for p in shards]
+    rep = shards[1].autotune(asg, reps=1)
+    assert all(t > 0 for t in rep["ms"])
+    assert bb.prove_partials(asg, shards[1]) == default_parts[1]                  # still the default form
+    for index in range(len(bb.tuning_names())):                                    # the SAME form on all shards: same proof
+        for p in shards:
+            p.apply_tuning(index)
+        assert bb.finalize(whole, [bb.prove_partials(asg, p) for p in shards], 5, 7) == proof, index
+    for p in shards + [whole]:
+        p.apply_tuning(0)
+        p.free()
 
 
 def test_emulated_table_forms_fuzz(worker):
