@@ -117,7 +117,15 @@ def autotune_sharded(assignment, params, r, s, device_ptrs=None, reps=3, group=N
                 raise
             ms.append(-2.0)
     chosen = min((i for i in range(len(names)) if ms[i] > 0), key=lambda i: ms[i])
-    params.apply_tuning(chosen)
+    ok = 1.0
+    try:
+        params.apply_tuning(chosen)
+    except BackendError:
+        ok = 0.0
+    if _all_reduce(ok, "MIN", group) < 1.0:              # (a table that no longer fits on one rank:) everybody back to the default
+        ms[chosen] = -1.0
+        chosen = 0
+        params.apply_tuning(0)
     HOST_MS.clear()
     return {"chosen": chosen, "name": names[chosen], "ms": ms}
 
