@@ -89,20 +89,15 @@ def test_tuner_child_mode_and_parent_fallback(tmp_path, emu_lib):
     """bench.py's sandboxed tuner: (1) child mode (--tune-child) builds the key and witness, tunes and prints its report --
     run here on the emulated device; (2) a parent whose child cannot run (the real library finds no CUDA device in this
     container) records the error and measures the default form."""
-    script = tmp_path / "child.py"
-    script.write_text(f"ROOT = {ROOT!r}\nEMU_LIB = {emu_lib!r}\nEXTRA = ['--tune-child']\n" + DRY_RUN)
-    res = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=900, cwd=ROOT)
-    assert res.returncode == 0, res.stderr[-3000:]
-    rep = json.loads([l for l in res.stdout.splitlines() if l.strip()][-1])["tune_child"]
-    assert all(t > 0 for t in rep["ms"]) and rep["ms"][rep["chosen"]] == min(rep["ms"]) and rep["name"]
-    # the child of rank 1 of 2 (the gate in front of the collective tuner): that rank's key shard, no process group
+    # (the unsharded tuner itself runs in the dry run above; here) the child of rank 1 of 2 -- the gate in front of the
+    # collective tuner: that rank's key shard, no process group
     script = tmp_path / "child_shard.py"
     script.write_text(f"ROOT = {ROOT!r}\nEMU_LIB = {emu_lib!r}\nEXTRA = ['--tune-child', '--shard-index', '1', '--shard-count', '2']\n" + DRY_RUN)
     env = dict(os.environ, WORLD_SIZE="2", RANK="1", LOCAL_RANK="0")
     res = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
     assert res.returncode == 0, res.stderr[-3000:]
     rep = json.loads([l for l in res.stdout.splitlines() if l.strip()][-1])["tune_child"]
-    assert all(t > 0 for t in rep["ms"])
+    assert all(t > 0 for t in rep["ms"]) and rep["name"]
     script = tmp_path / "parent.py"
     script.write_text(f"ROOT = {ROOT!r}\nEMU_LIB = {emu_lib!r}\nEXTRA = ['--autotune', '1', '--no-cpu-baseline']\n" + DRY_RUN)
     res = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=900, cwd=ROOT)

