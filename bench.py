@@ -11,6 +11,10 @@ already resident in HBM; `e2e` goes through the public call with pinned HOST buf
 inside the timed region.  Other workloads (--workload msm | ntt) are the microbenches of
 configs[2] and configs[3].
 
+Before the warm-up the MSM form is chosen by measurement on the key about to be timed: at N = 1 by
+bb_groth16_autotune in a child process, at N > 1 by the collective tuner behind per-rank child probes; the timed steps
+run the chosen form only and the line records every form's milliseconds under `autotune` (--autotune 0: default form).
+
 The oracle (oracle/) is used only by the cpu_baseline leg and by --impl reference.
 """
 import argparse
