@@ -345,7 +345,11 @@ def run_prove(args):
             raise SystemExit("launch with torch.distributed.run for --gpus > 1")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        backend = os.environ.get("BB_BENCH_DIST_BACKEND", "nccl")         # gloo: the CPU dry run of tests/test_bench_contract.py
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
     log_n = args.log_size or 20
     rounds = (1 << (log_n - 1)) - 1
     worker = bb.Worker(local)
@@ -445,9 +449,8 @@ def run_prove(args):
         sync()
         dt = time.perf_counter() - t0
         if world > 1:
-            t = torch.tensor([dt], device=f"cuda:{local}", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+            from bellman_b200.distributed import max_over_ranks
+            dt = max_over_ranks(dt)
         h1, d1 = worker.bytes_copied()
         return dt, proof, worker.kernel_launches - l0, (h1 - h0) / steps, (d1 - d0) / steps
 

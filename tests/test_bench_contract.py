@@ -52,6 +52,8 @@ torch.Tensor.to = lambda self, *a, **k: self if (a and isinstance(a[0], str) and
 torch.Tensor.pin_memory = lambda self, *a, **k: self
 import bellman_b200 as bb
 bb.LIB_PATH, bb._lib = EMU_LIB, None          # the product sources on host fibers (tests/native)
+import os
+os.environ["LOCAL_RANK"] = "0"                # the emulation has one device: under torchrun every rank uses it
 spec = importlib.util.spec_from_file_location("bench", ROOT + "/bench.py")
 bench = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(bench)
@@ -106,6 +108,27 @@ def test_tuner_child_mode_and_parent_fallback(tmp_path, emu_lib):
     at = d["autotune"]
     assert at["error"] and at["chosen"] == 0 and at["where"] == "child process" and "tuner process failed" in d["config"]["msm_form"]
     assert d["value"] > 0 and d["gpu_launches"] > 100
+
+
+def test_own_arm_dry_run_two_ranks(tmp_path, emu_lib):
+    """bench.py --gpus 2 under torchrun with gloo and the emulated device: the sharded step, the max over ranks, the gate in
+    front of the collective tuner (the per-rank tuner children cannot run here -- no CUDA device -- so both ranks must stay on
+    the default form and say why), the sharded proof == single-GPU proof check, one JSON line from rank 0."""
+    script = tmp_path / "dry2.py"
+    script.write_text(f"ROOT = {ROOT!r}\nEMU_LIB = {emu_lib!r}\nEXTRA = ['--gpus', '2', '--autotune', '1', '--no-cpu-baseline']\n" + DRY_RUN)
+    env = dict(os.environ, BB_BENCH_DIST_BACKEND="gloo")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+    assert res.returncode == 0, res.stderr[-3000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip().startswith("{")]
+    assert len(lines) == 1, res.stdout
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["scaling"] == "strong" and d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert "sharded proof == single-GPU proof" in d["proof_check"] and len(d["proof_sha256"]) == 64
+    at = d["autotune"]
+    assert at["chosen"] == 0 and at["error"] and "tuner process failed" in d["config"]["msm_form"]
+    assert set(d["sharded_host_ms_per_step"]) >= {"queue_witness_msms", "all_gather"}
 
 
 def test_msm_microbench_dry_run_on_the_emulated_device(tmp_path, emu_lib):
